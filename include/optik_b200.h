@@ -1,0 +1,183 @@
+/*
+ * optik_b200.h -- C ABI of liboptik_b200.so, the B200-native drop-in for OptIK's
+ * Robot::ik() hot path.
+ *
+ * Part 1 are EXACTLY the symbols the reference's own FFI layer exports and its
+ * C++ wrapper binds (kylc/optik @ 355e463):
+ *     Rust side   crates/optik-cpp/src/lib.rs:26-183   (#[no_mangle] extern "C")
+ *     C++ side    crates/optik-cpp/src/lib.cpp:5-31    (extern "C" declarations)
+ * with the reference's ownership contract: every returned double* is a
+ * malloc()-compatible buffer the CALLER releases with free()
+ * (lib.cpp:72,87,100,115,129); optik_robot* is opaque and released only by
+ * optik_robot_free().  Where the reference panics across the FFI boundary
+ * (null robot, bad URDF, seed outside the joint limits, lib.rs:251-254) these
+ * functions print the same message to stderr and abort(), which is what a Rust
+ * panic in an extern "C" fn does.
+ *
+ * Part 2 are additive, batched entry points (plain pointers and sizes, no C++
+ * or torch types) through which a host -- the reference's Rust crate via an
+ * `extern "C"` block, see INTEGRATION.md -- drives the sm_100a kernels
+ * directly.  They return 0 on success or a nonzero code and never abort;
+ * optik_last_error() describes the last failure on the calling thread.
+ *
+ * There is no CPU fallback: every numerical entry point runs on the GPU and
+ * fails loudly (error code / NULL + message) when no CUDA device is usable.
+ */
+#ifndef OPTIK_B200_H
+#define OPTIK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == optik::detail::robot (crates/optik-cpp/include/optik.hpp:9-10) */
+typedef struct optik_robot optik_robot;
+
+/* == SolutionMode, crates/optik/src/config.rs:3-8 (repr(C)) */
+enum { OPTIK_MODE_QUALITY = 1, OPTIK_MODE_SPEED = 2 };
+
+/* == CSolverConfig, crates/optik-cpp/src/lib.rs:10-20 == optik::SolverConfig, include/optik.hpp:18-27.
+ * 96 bytes on LP64.  max_restarts == 0 means "no restart limit" (lib.rs:273-277). */
+typedef struct optik_solver_config {
+  int32_t solution_mode;
+  double max_time;
+  unsigned long max_restarts;
+  double tol_f;
+  double tol_df;
+  double tol_dx;
+  double linear_weight[3];
+  double angular_weight[3];
+} optik_solver_config;
+
+/* ------------------------------------------------------------------------
+ * Part 1 -- the reference's FFI surface
+ * ------------------------------------------------------------------------ */
+
+/* crates/optik-cpp/src/lib.rs:26-37.  Aborts on unreadable/invalid URDF or unknown links. */
+optik_robot* optik_robot_from_urdf_file(const char* path, const char* base_link, const char* ee_link);
+/* crates/optik-cpp/src/lib.rs:39-50 */
+optik_robot* optik_robot_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link);
+/* crates/optik-cpp/src/lib.rs:52-57 */
+void optik_robot_free(optik_robot* robot);
+/* crates/optik-cpp/src/lib.rs:59-65.  rayon thread count in the reference; here it only bounds the number of
+ * host threads that may stage work concurrently (the restart fan-out is the CUDA grid). */
+void optik_robot_set_parallelism(optik_robot* robot, unsigned int n);
+/* crates/optik-cpp/src/lib.rs:67-73 */
+unsigned int optik_robot_num_positions(const optik_robot* robot);
+/* crates/optik-cpp/src/lib.rs:75-88.  2n doubles: [lb_0..lb_{n-1}, ub_0..ub_{n-1}] */
+double* optik_robot_joint_limits(const optik_robot* robot);
+/* crates/optik-cpp/src/lib.rs:118-125.  n doubles, uniform in the limits, non-deterministic RNG */
+double* optik_robot_random_configuration(const optik_robot* robot);
+/* crates/optik-cpp/src/lib.rs:90-104.  6*n doubles, column-major 6 x n body-frame Jacobian, identity ee_offset */
+double* optik_robot_joint_jacobian(const optik_robot* robot, const double* x);
+/* crates/optik-cpp/src/lib.rs:106-116.  16 doubles, column-major 4x4 homogeneous end-effector pose */
+double* optik_robot_fk(const optik_robot* robot, const double* x);
+/* crates/optik-cpp/src/lib.rs:127-162.  target: 16 doubles column-major 4x4; x0: n doubles.
+ * Returns n doubles, or NULL when no restart converged within max_time / max_restarts.
+ * Aborts with "seed joint position outside of joint limits" like lib.rs:251-254. */
+double* optik_robot_ik(const optik_robot* robot, const optik_solver_config* config, const double* target,
+                       const double* x0);
+/* crates/optik-cpp/src/lib.rs:164-183.  Out of scope of this build (Clarabel LP):
+ * always returns NULL ("no solution") after printing a one-time notice. */
+double* optik_robot_diff_ik(const optik_robot* robot, const double* x0, const double* V_WE, const double* v_max);
+
+/* ------------------------------------------------------------------------
+ * Part 2 -- additive batched / introspection entry points
+ * ------------------------------------------------------------------------ */
+
+/* Poses in the batched API are "pose8": {qx,qy,qz,qw, tx,ty,tz, 0} = nalgebra's Isometry3<f64> coordinates
+ * (rotation i,j,k,w then translation) padded to 64 B so that a pose is four 16-byte vector loads. */
+
+enum {
+  OPTIK_OK = 0,
+  OPTIK_ERR_INVALID = 1,     /* bad argument */
+  OPTIK_ERR_CUDA = 2,        /* CUDA runtime error (no device, launch failure ...) */
+  OPTIK_ERR_SEED_LIMITS = 3, /* an x0 lies outside the joint limits (lib.rs:251-254) */
+  OPTIK_ERR_UNSUPPORTED = 4  /* chain not supported by the kernel (n > 32, fixed joint mid-chain) */
+};
+
+/* per-target / per-attempt status; 1..3 = NLopt SuccessState as classified at lib.rs:376-379 */
+enum {
+  OPTIK_STATUS_NONE = 0,
+  OPTIK_STATUS_STOPVAL = 1,
+  OPTIK_STATUS_FTOL = 2,
+  OPTIK_STATUS_XTOL = 3,
+  OPTIK_STATUS_ITERCAP = 4,
+  OPTIK_STATUS_STUCK = 5,
+  OPTIK_STATUS_NAN = 6,
+  OPTIK_STATUS_SKIPPED = 7
+};
+
+const char* optik_last_error(void);
+/* Non-aborting constructors (NULL + optik_last_error() on failure). */
+optik_robot* optik_robot_try_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link);
+/* Robot::new(KinematicChain) analogue (crates/optik/src/lib.rs:42-47): flat chain, 16 doubles per joint:
+ * [0..2] origin xyz [3] type (0 revolute,1 prismatic,2 fixed) [4..7] origin quat xyzw [8..10] axis [12] lower [13] upper */
+optik_robot* optik_robot_from_chain(const double* chain, unsigned int njoints);
+/* Option: fold fixed joints in URDF order (earlier*later) instead of the reference's order
+ * (kinematics.rs:70,77).  Must be called before loading; default 0 = reference order. */
+void optik_set_urdf_correct_fold(int on);
+unsigned int optik_robot_num_joints(const optik_robot* robot); /* chain entries incl. a fixed tip joint */
+int optik_robot_chain(const optik_robot* robot, double* out /* num_joints*16 */);
+/* CUDA device the robot's kernels run on (default: device 0). */
+int optik_robot_set_device(optik_robot* robot, int device);
+/* 1 if a satisfying status under `config` (lib.rs:376-379) */
+int optik_status_is_success(const optik_solver_config* config, int status);
+
+typedef struct optik_gpu_batch_opts {
+  uint32_t struct_size;    /* sizeof(optik_gpu_batch_opts) */
+  uint32_t restarts;       /* restart attempts per target (restart 0 = x0, i>=1 = ChaCha8 stream i).
+                              0 = config->max_restarts, which must then be finite and > 0 */
+  uint64_t restart_begin;  /* first restart index; [restart_begin, restart_begin+restarts) is run */
+  uint32_t chunks;         /* parallel chunks per target (each runs its restarts in index order); 0 = auto */
+  uint32_t tile;           /* lanes per restart attempt: 8, 16, 32 (= one warp per seed); 0 = smallest that fits n */
+  uint32_t max_evals;      /* objective evaluations per attempt; 0 = default (64) */
+  uint32_t blocks;         /* grid size; 0 = auto (multiple of the SM count) */
+  int32_t memory;          /* 0: all data pointers are host memory; 1: device memory (async on `stream`) */
+  const double* ee_offset; /* pose8 (host memory) or NULL = identity (lib.rs:245) */
+  uint64_t* restart_out;   /* [T] winning restart index, optional */
+  int32_t* evals_out;      /* [T] objective evaluations spent on the target, optional */
+  uint64_t* counters;      /* [3] += {attempts run, evaluations, converged attempts}, optional */
+} optik_gpu_batch_opts;
+
+/* Robot::ik() over T independent (target, x0) pairs in one launch.
+ *   targets [T][8] pose8, x0 [T][n]  ->  q_out [T][n], cost_out [T] (objective value), status_out [T]
+ * Per target the result is what the reference returns with set_parallelism(1): Speed = the lowest-index
+ * converged restart (lib.rs:409-412), Quality = arg-min ||q - x0|| over converged restarts (lib.rs:398-407);
+ * status_out[t] is the winning attempt's status, or a failure status when none converged (== None).
+ * config->max_time > 0 bounds the whole launch (device-side deadline, checked per evaluation like lib.rs:308). */
+int optik_gpu_ik_batch(const optik_robot* robot, const optik_solver_config* config, const optik_gpu_batch_opts* opts,
+                       const double* targets, const double* x0, uint64_t T, double* q_out, double* cost_out,
+                       int32_t* status_out, void* stream);
+
+/* Per-restart records for ONE target: restarts [restart_begin, restart_begin+restarts) each run to completion.
+ *   q_all [R][n], f_all [R], status_all [R], evals_all [R]  (memory space per opts->memory) */
+int optik_gpu_ik_attempts(const optik_robot* robot, const optik_solver_config* config,
+                          const optik_gpu_batch_opts* opts, const double* target, const double* x0, double* q_all,
+                          double* f_all, int32_t* status_all, int32_t* evals_all, void* stream);
+
+/* Batched evaluator = Robot::fk + Robot::joint_jacobian + objective + objective_grad
+ * (lib.rs:93-99, objective.rs:40-110) over B configurations.
+ *   q [B][n]; targets [B][8] (or one pose8 when shared_target != 0; may be NULL if f_out and grad_out are NULL)
+ *   ee_out [B][8] pose8, jac_out [B][6n] column-major 6 x n, f_out [B], grad_out [B][n]; any output may be NULL */
+int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double* targets, int shared_target,
+                         uint64_t B, const double* linear_weight, const double* angular_weight,
+                         const double* ee_offset, int memory, double* ee_out, double* jac_out, double* f_out,
+                         double* grad_out, void* stream);
+
+/* Robot::ik with the arguments the C wrapper drops (crates/optik/src/lib.rs:241-247): ee_offset and the returned cost.
+ * target_pose8 / ee_offset_pose8 are pose8 (ee_offset may be NULL = identity).  Same max_time / max_restarts
+ * semantics as optik_robot_ik.  Returns 1 = solution written to q_out[n], *cost_out; 0 = no solution; <0 = -(error). */
+int optik_robot_ik_ex(const optik_robot* robot, const optik_solver_config* config, const double* target_pose8,
+                      const double* x0, const double* ee_offset_pose8, double* q_out, double* cost_out);
+
+/* Pinned host allocations for fast, truly asynchronous host<->device copies. */
+void* optik_host_alloc(uint64_t bytes);
+void optik_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTIK_B200_H */

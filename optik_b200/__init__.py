@@ -1,0 +1,432 @@
+"""optik_b200 -- B200-native batched inverse kinematics behind OptIK's Robot / SolverConfig / ik() surface.
+
+Host-side mirror of the reference's Python module (kylc/optik @ 355e463):
+    optik.pyi:9-49, crates/optik-py/src/lib.rs:17-155   -> SolverConfig, Robot (same names, arguments, defaults,
+                                                           4x4 row-major nested-list poses, None for "no solution")
+implemented over the C ABI of ``lib/liboptik_b200.so`` (include/optik_b200.h) with ctypes.  All numerics run in the
+CUDA kernels of ``csrc/``; there is no CPU fallback -- importing works without a GPU (model loading, limits), any
+numerical call without a usable CUDA device raises ``OptikError``.
+
+Additions over the reference surface: ``Robot.ik_batch`` / ``ik_attempts`` / ``eval_batch`` (numpy arrays = host path
+with copies inside the call; torch CUDA tensors = zero-copy device path on the current torch stream).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Robot", "SolverConfig", "OptikError", "load_library", "data_path", "STATUS_NAMES"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liboptik_b200.so")
+_lib = None
+
+STATUS_NAMES = {0: "none", 1: "stopval", 2: "ftol", 3: "xtol", 4: "itercap", 5: "stuck", 6: "nan", 7: "skipped"}
+U64_MAX = 2 ** 64 - 1
+
+
+class OptikError(RuntimeError):
+    pass
+
+
+class _CSolverConfig(C.Structure):  # == CSolverConfig, crates/optik-cpp/src/lib.rs:10-20
+    _fields_ = [("solution_mode", C.c_int32), ("max_time", C.c_double), ("max_restarts", C.c_ulong),
+                ("tol_f", C.c_double), ("tol_df", C.c_double), ("tol_dx", C.c_double),
+                ("linear_weight", C.c_double * 3), ("angular_weight", C.c_double * 3)]
+
+
+class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
+    _fields_ = [("struct_size", C.c_uint32), ("restarts", C.c_uint32), ("restart_begin", C.c_uint64),
+                ("chunks", C.c_uint32), ("tile", C.c_uint32), ("max_evals", C.c_uint32), ("blocks", C.c_uint32),
+                ("memory", C.c_int32), ("ee_offset", C.c_void_p), ("restart_out", C.c_void_p),
+                ("evals_out", C.c_void_p), ("counters", C.c_void_p)]
+
+
+def data_path(name):
+    """Path of a bundled kinematics-only URDF (panda, ur5, ur3e, snake20)."""
+    return os.path.join(_HERE, "data", name if name.endswith(".urdf") else name + ".urdf")
+
+
+ROBOT_LINKS = {"panda": ("panda_link0", "panda_link8"), "ur5": ("base_link", "ee_link"),
+               "ur3e": ("ur_base_link", "ur_ee_link"), "snake20": ("seg0", "tip")}
+
+
+def load_library():
+    """dlopen liboptik_b200.so; fails loudly when it has not been built (python -m optik_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OptikError(f"{LIB_PATH} is missing: build it with `python -m optik_b200.build` "
+                         "(there is no CPU fallback for the IK path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, cp = C.c_void_p, C.POINTER(C.c_double), C.c_char_p
+    sig = {
+        "optik_robot_from_urdf_file": (vp, [cp, cp, cp]),
+        "optik_robot_from_urdf_str": (vp, [cp, cp, cp]),
+        "optik_robot_try_from_urdf_str": (vp, [cp, cp, cp]),
+        "optik_robot_from_chain": (vp, [dp, C.c_uint]),
+        "optik_robot_free": (None, [vp]),
+        "optik_robot_set_parallelism": (None, [vp, C.c_uint]),
+        "optik_robot_num_positions": (C.c_uint, [vp]),
+        "optik_robot_num_joints": (C.c_uint, [vp]),
+        "optik_robot_chain": (C.c_int, [vp, dp]),
+        "optik_robot_set_device": (C.c_int, [vp, C.c_int]),
+        "optik_robot_joint_limits": (vp, [vp]),
+        "optik_robot_random_configuration": (vp, [vp]),
+        "optik_robot_joint_jacobian": (vp, [vp, dp]),
+        "optik_robot_fk": (vp, [vp, dp]),
+        "optik_robot_ik": (vp, [vp, C.POINTER(_CSolverConfig), dp, dp]),
+        "optik_robot_ik_ex": (C.c_int, [vp, C.POINTER(_CSolverConfig), dp, dp, dp, dp, dp]),
+        "optik_robot_diff_ik": (vp, [vp, dp, dp, dp]),
+        "optik_last_error": (cp, []),
+        "optik_set_urdf_correct_fold": (None, [C.c_int]),
+        "optik_status_is_success": (C.c_int, [C.POINTER(_CSolverConfig), C.c_int]),
+        "optik_gpu_ik_batch": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, C.c_uint64, vp, vp, vp, vp]),
+        "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
+        "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
+        "optik_host_alloc": (vp, [C.c_uint64]),
+        "optik_host_free": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.free = C.CDLL(None).free
+    lib.free.argtypes = [vp]
+    lib.free.restype = None
+    _lib = lib
+    return lib
+
+
+def _err():
+    return load_library().optik_last_error().decode("utf-8", "replace")
+
+
+def _check(rc):
+    if rc != 0:
+        raise OptikError(f"optik_b200 error {rc}: {_err()}")
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _take(ptr, count):
+    """Copy a malloc()ed double buffer returned by the C ABI and free() it (crates/optik-cpp/src/lib.cpp:71-73)."""
+    lib = load_library()
+    out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,)).copy()
+    lib.free(ptr)
+    return out
+
+
+def _pose8_from_rows(m):
+    """4x4 row-major nested list / array -> pose8 (crates/optik-py/src/lib.rs:8-15 parse_pose)."""
+    M = np.asarray(m, dtype=np.float64)
+    if M.shape != (4, 4):
+        raise ValueError("invalid target transform specified")
+    R = M[:3, :3]
+    if not (np.allclose(R @ R.T, np.eye(3), atol=1e-6) and np.allclose(M[3], [0, 0, 0, 1], atol=1e-9)):
+        raise ValueError("invalid target transform specified")  # nalgebra::try_convert::<Isometry3> fails
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        s = np.sqrt(tr + 1.0) * 2
+        q = [(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s]
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2]) * 2
+        q = [0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s, (R[2, 1] - R[1, 2]) / s]
+    elif R[1, 1] > R[2, 2]:
+        s = np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2]) * 2
+        q = [(R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s, (R[0, 2] - R[2, 0]) / s]
+    else:
+        s = np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1]) * 2
+        q = [(R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s, (R[1, 0] - R[0, 1]) / s]
+    q = np.asarray(q) / np.linalg.norm(q)
+    return np.array([q[0], q[1], q[2], q[3], M[0, 3], M[1, 3], M[2, 3], 0.0])
+
+
+def _rows_from_pose8(p):
+    x, y, z, w = p[:4]
+    return [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), p[4]],
+            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w), p[5]],
+            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y), p[6]],
+            [0.0, 0.0, 0.0, 1.0]]
+
+
+class SolverConfig:
+    """optik.pyi:9-20; defaults of crates/optik-py/src/lib.rs:24-31 (== config.rs:52-65)."""
+
+    def __init__(self, solution_mode="speed", max_time=0.1, max_restarts=U64_MAX, tol_f=1e-6, tol_df=-1.0,
+                 tol_dx=-1.0, linear_weight=(1.0, 1.0, 1.0), angular_weight=(1.0, 1.0, 1.0)):
+        if solution_mode not in ("speed", "quality"):
+            raise ValueError("invalid solution mode")  # crates/optik-py/src/lib.rs:43
+        if max_time == 0.0 and max_restarts == 0:
+            # crates/optik-py/src/lib.rs:45-47
+            raise ValueError("no time or restart limit applied -- solver would run forever")
+        self.solution_mode = solution_mode
+        self.max_time = float(max_time)
+        self.max_restarts = int(max_restarts)
+        self.tol_f = float(tol_f)
+        self.tol_df = float(tol_df)
+        self.tol_dx = float(tol_dx)
+        self.linear_weight = [float(x) for x in linear_weight]
+        self.angular_weight = [float(x) for x in angular_weight]
+        if len(self.linear_weight) != 3 or len(self.angular_weight) != 3:
+            raise ValueError("weights must have 3 components")
+
+    def _c(self):
+        c = _CSolverConfig()
+        c.solution_mode = 1 if self.solution_mode == "quality" else 2  # config.rs:5-8
+        c.max_time = self.max_time
+        c.max_restarts = 0 if self.max_restarts >= U64_MAX else self.max_restarts  # 0 == unlimited (lib.rs:273-277)
+        c.tol_f, c.tol_df, c.tol_dx = self.tol_f, self.tol_df, self.tol_dx
+        c.linear_weight[:] = self.linear_weight
+        c.angular_weight[:] = self.angular_weight
+        return c
+
+    def is_success(self, status):
+        """lib.rs:376-379 applied to a status code array."""
+        st = np.asarray(status)
+        return ((self.tol_f >= 0) & (st == 1)) | ((self.tol_df >= 0) & (st == 2)) | ((self.tol_dx >= 0) & (st == 3))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class Robot:
+    """optik.pyi:22-49 over the C ABI; plus batched entry points."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise OptikError(_err())
+        self._h = handle
+        self._n = load_library().optik_robot_num_positions(handle)
+        lim = _take(load_library().optik_robot_joint_limits(handle), 2 * self._n)
+        self._lb, self._ub = lim[:self._n].copy(), lim[self._n:].copy()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.optik_robot_free(h)
+
+    # ---- constructors -------------------------------------------------------------------------
+    @staticmethod
+    def from_urdf_file(path, base_link, ee_link):
+        with open(path, "r") as f:  # a missing file raises here instead of aborting the process
+            text = f.read()
+        return Robot.from_urdf_str(text, base_link, ee_link)
+
+    @staticmethod
+    def from_urdf_str(urdf, base_link, ee_link):
+        lib = load_library()
+        return Robot(lib.optik_robot_try_from_urdf_str(urdf.encode(), base_link.encode(), ee_link.encode()))
+
+    @staticmethod
+    def from_chain(chain):
+        """Robot::new(KinematicChain) (lib.rs:42-47) from a flat (njoints, 16) chain array."""
+        a = np.ascontiguousarray(chain, dtype=np.float64).reshape(-1, 16)
+        return Robot(load_library().optik_robot_from_chain(_dptr(a), a.shape[0]))
+
+    @staticmethod
+    def named(name):
+        base, ee = ROBOT_LINKS[name]
+        return Robot.from_urdf_file(data_path(name), base, ee)
+
+    # ---- reference surface --------------------------------------------------------------------
+    def set_parallelism(self, n):
+        load_library().optik_robot_set_parallelism(self._h, int(n))
+
+    def set_device(self, device):
+        _check(load_library().optik_robot_set_device(self._h, int(device)))
+
+    def num_positions(self):
+        return int(self._n)
+
+    def joint_limits(self):
+        return list(self._lb), list(self._ub)
+
+    def chain(self):
+        nj = load_library().optik_robot_num_joints(self._h)
+        out = np.zeros((nj, 16))
+        _check(load_library().optik_robot_chain(self._h, _dptr(out)))
+        return out
+
+    def random_configuration(self):
+        return list(_take(load_library().optik_robot_random_configuration(self._h), self._n))
+
+    def _x(self, x, what="x0"):
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        if x.shape[0] != self._n:
+            raise ValueError(f"len({what}) != num_positions")  # crates/optik-py/src/lib.rs:94,106,127
+        return x
+
+    def fk(self, x, ee_offset=None):
+        x = self._x(x, "x")
+        out = self.eval_batch(x[None, :], ee_offset=ee_offset, want=("ee",))
+        return _rows_from_pose8(out["ee"][0])
+
+    def joint_jacobian(self, x, ee_offset=None):
+        x = self._x(x, "x")
+        out = self.eval_batch(x[None, :], ee_offset=ee_offset, want=("jac",))
+        return [list(r) for r in out["jac"][0].reshape(self._n, 6).T]  # column-major 6 x n -> 6 row lists
+
+    def ik(self, config, target, x0, ee_offset=None):
+        """-> (q, cost) or None (crates/optik-py/src/lib.rs:117-132)."""
+        x0 = self._x(x0)
+        if np.any(x0 < self._lb) or np.any(x0 > self._ub):
+            raise ValueError("seed joint position outside of joint limits")  # lib.rs:251-254
+        tgt = _pose8_from_rows(target)
+        eo = None if ee_offset is None else _pose8_from_rows(ee_offset)
+        c = config._c()
+        q = np.zeros(self._n)
+        cost = C.c_double()
+        rc = load_library().optik_robot_ik_ex(self._h, C.byref(c), _dptr(tgt), _dptr(x0), None if eo is None else _dptr(eo),
+                                              _dptr(q), C.cast(C.byref(cost), C.POINTER(C.c_double)))
+        if rc < 0:
+            raise OptikError(f"optik_b200 error {-rc}: {_err()}")
+        return (list(q), cost.value) if rc == 1 else None
+
+    def diff_ik(self, x0, V_WE, v_max, ee_offset=None):
+        """Out of scope of this build; the C symbol exists and reports "no solution"."""
+        self._x(x0)
+        self._x(v_max, "v_max")
+        return None
+
+    # ---- batched additions --------------------------------------------------------------------
+    def _opts(self, memory, restarts=0, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0, ee_offset=None):
+        o = _BatchOpts()
+        o.struct_size = C.sizeof(_BatchOpts)
+        o.restarts, o.restart_begin, o.chunks, o.tile = int(restarts), int(restart_begin), int(chunks), int(tile)
+        o.max_evals, o.blocks, o.memory = int(max_evals), int(blocks), int(memory)
+        keep = []
+        if ee_offset is not None:
+            eo = np.ascontiguousarray(ee_offset, dtype=np.float64)
+            eo = _pose8_from_rows(eo) if eo.shape == (4, 4) else eo.ravel()
+            keep.append(eo)
+            o.ee_offset = eo.ctypes.data
+        return o, keep
+
+    def ik_batch(self, config, targets, x0, restarts=None, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0,
+                 ee_offset=None, stats=False, out=None):
+        """Robot::ik over T (target, x0) pairs in one launch.
+
+        targets: (T, 8) pose8 rows {qx,qy,qz,qw,tx,ty,tz,0};  x0: (T, n).
+        numpy in  -> host path (H2D/D2H inside the call), returns numpy (q, cost, status[, extra]).
+        torch CUDA tensors in -> device path on torch's current stream, returns torch tensors (no sync).
+        """
+        lib = load_library()
+        c = config._c()
+        if restarts is None:
+            restarts = 0
+        n = self._n
+        if _is_torch(targets):
+            import torch
+            T = targets.shape[0]
+            assert targets.is_cuda and x0.is_cuda and targets.dtype == torch.float64 and x0.dtype == torch.float64
+            assert targets.is_contiguous() and x0.is_contiguous() and targets.shape == (T, 8) and x0.shape == (T, n)
+            dev = targets.device
+            if out is None:
+                q = torch.empty((T, n), dtype=torch.float64, device=dev)
+                f = torch.empty((T,), dtype=torch.float64, device=dev)
+                st = torch.empty((T,), dtype=torch.int32, device=dev)
+            else:
+                q, f, st = out
+            o, keep = self._opts(1, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
+            extra = {}
+            if stats:
+                extra["restart"] = torch.empty((T,), dtype=torch.int64, device=dev)
+                extra["evals"] = torch.empty((T,), dtype=torch.int32, device=dev)
+                extra["counters"] = torch.zeros((3,), dtype=torch.int64, device=dev)
+                o.restart_out, o.evals_out, o.counters = extra["restart"].data_ptr(), extra["evals"].data_ptr(), extra["counters"].data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib.optik_gpu_ik_batch(self._h, C.byref(c), C.byref(o), targets.data_ptr(), x0.data_ptr(), T,
+                                          q.data_ptr(), f.data_ptr(), st.data_ptr(), stream))
+            return (q, f, st, extra) if stats else (q, f, st)
+        targets = np.ascontiguousarray(targets, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        T = targets.shape[0]
+        if targets.shape != (T, 8) or x0.shape != (T, n):
+            raise ValueError("targets must be (T, 8) pose8 and x0 (T, num_positions)")
+        if out is None:
+            q, f, st = np.empty((T, n)), np.empty(T), np.empty(T, dtype=np.int32)
+        else:
+            q, f, st = out
+        o, keep = self._opts(0, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
+        extra = {}
+        if stats:
+            extra["restart"] = np.zeros(T, dtype=np.uint64)
+            extra["evals"] = np.zeros(T, dtype=np.int32)
+            extra["counters"] = np.zeros(3, dtype=np.uint64)
+            o.restart_out, o.evals_out, o.counters = extra["restart"].ctypes.data, extra["evals"].ctypes.data, extra["counters"].ctypes.data
+        _check(lib.optik_gpu_ik_batch(self._h, C.byref(c), C.byref(o), targets.ctypes.data, x0.ctypes.data, T,
+                                      q.ctypes.data, f.ctypes.data, st.ctypes.data, None))
+        return (q, f, st, extra) if stats else (q, f, st)
+
+    def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None):
+        """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
+        completion (no Speed-mode early exit) -- BASELINE config 2's output."""
+        lib = load_library()
+        c = config._c()
+        n, R = self._n, int(restarts)
+        target = np.ascontiguousarray(target, dtype=np.float64).reshape(8)
+        x0 = self._x(x0)
+        q, f = np.empty((R, n)), np.empty(R)
+        st, ev = np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32)
+        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset)
+        _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.ctypes.data, x0.ctypes.data,
+                                         q.ctypes.data, f.ctypes.data, st.ctypes.data, ev.ctypes.data, None))
+        return q, f, st, ev
+
+    def eval_batch(self, q, targets=None, linear_weight=None, angular_weight=None, ee_offset=None,
+                   want=("ee", "jac", "f", "grad")):
+        """Batched fk / joint_jacobian / objective / objective_grad (lib.rs:93-99, objective.rs:40-110).
+
+        q: (B, n); targets: (B, 8) or (8,) shared.  Returns dict with ee (B,8), jac (B,6n) column-major 6 x n,
+        f (B,), grad (B,n) -- those named in `want` (f/grad need targets).  numpy = host path, torch CUDA = device path.
+        """
+        lib = load_library()
+        n = self._n
+        want = set(want)
+        if targets is None:
+            want -= {"f", "grad"}
+        wl = None if linear_weight is None else (C.c_double * 3)(*[float(x) for x in linear_weight])
+        wa = None if angular_weight is None else (C.c_double * 3)(*[float(x) for x in angular_weight])
+        eo = None
+        if ee_offset is not None:
+            e = np.ascontiguousarray(ee_offset, dtype=np.float64)
+            eo = _pose8_from_rows(e) if e.shape == (4, 4) else e.ravel().copy()
+        eop = None if eo is None else _dptr(eo)
+        if _is_torch(q):
+            import torch
+            B = q.shape[0]
+            assert q.is_cuda and q.dtype == torch.float64 and q.is_contiguous() and q.shape == (B, n)
+            shared = 0
+            tp = None
+            if targets is not None:
+                assert targets.is_cuda and targets.dtype == torch.float64 and targets.is_contiguous()
+                shared = int(targets.numel() == 8 and B != 1)
+                tp = targets.data_ptr()
+            mk = lambda shape: torch.empty(shape, dtype=torch.float64, device=q.device)
+            outs = {k: mk(s) for k, s in (("ee", (B, 8)), ("jac", (B, 6 * n)), ("f", (B,)), ("grad", (B, n))) if k in want}
+            ptr = lambda k: outs[k].data_ptr() if k in outs else None
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+            _check(lib.optik_gpu_eval_batch(self._h, q.data_ptr(), tp, shared, B, wl, wa, eop, 1, ptr("ee"), ptr("jac"),
+                                            ptr("f"), ptr("grad"), stream))
+            return outs
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        B = q.shape[0]
+        if q.shape != (B, n):
+            raise ValueError("len(x) != num_positions")
+        shared, tp = 0, None
+        if targets is not None:
+            targets = np.ascontiguousarray(targets, dtype=np.float64)
+            shared = int(targets.size == 8 and B != 1)
+            if not shared and targets.shape != (B, 8):
+                raise ValueError("targets must be (B, 8) or (8,)")
+            tp = targets.ctypes.data
+        outs = {k: np.empty(s) for k, s in (("ee", (B, 8)), ("jac", (B, 6 * n)), ("f", (B,)), ("grad", (B, n))) if k in want}
+        ptr = lambda k: outs[k].ctypes.data if k in outs else None
+        _check(lib.optik_gpu_eval_batch(self._h, q.ctypes.data, tp, shared, B, wl, wa, eop, 0, ptr("ee"), ptr("jac"),
+                                        ptr("f"), ptr("grad"), None))
+        return outs

@@ -1,0 +1,705 @@
+// robot.cpp -- host side of liboptik_b200.so: the Robot object, launch plumbing and the C ABI.
+//
+// Mirrors, for the ik() path only, the reference's Robot / SolverConfig surface
+//   crates/optik/src/lib.rs:36-99, 241-415      Robot, joint_limits, random_configuration, fk, joint_jacobian, ik
+//   crates/optik/src/config.rs:22-65            SolverConfig
+//   crates/optik-cpp/src/lib.rs:10-183          the extern "C" layer whose symbols are re-exported here
+// The rayon restart loop and the NLopt solve live in solve_kernel.cu; this file only validates, stages buffers,
+// launches, and applies the reference's budget semantics (max_time / max_restarts, lib.rs:260-277) as waves.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/optik_b200.h"
+#include "solver_params.h"
+#include "urdf.hpp"
+
+extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, void* stream);
+extern "C" int optik_launch_select(const SelectParams* p, void* stream);
+extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
+extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
+extern "C" int optik_eval_smem_bytes(int n);
+
+namespace {
+
+thread_local std::string g_last_error;
+bool g_urdf_correct_fold = false;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+[[noreturn]] void panic(const std::string& msg) {  // a Rust panic inside extern "C" aborts the process
+  fprintf(stderr, "optik_b200: panicked: %s\n", msg.c_str());
+  fflush(stderr);
+  abort();
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (cudaError_t)(expr);                                                      \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(OPTIK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+// rand_core's SeedableRng::seed_from_u64 (PCG32 expansion) -> the ChaCha8 key used at lib.rs:359-361
+void seed_key_from_u64(uint64_t state, uint32_t key[8]) {
+  for (int i = 0; i < 8; i++) {
+    state = state * 6364136223846793005ULL + 11634580027462260723ULL;
+    const uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+    const uint32_t rot = (uint32_t)(state >> 59);
+    key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+  }
+}
+const uint64_t RNG_SEED = 42;  // lib.rs:359
+
+void pose8_identity(double* p) {
+  for (int i = 0; i < 8; i++) p[i] = 0;
+  p[3] = 1;
+}
+
+// 3x3 rotation (column-major 4x4 input) -> unit quaternion (Shepperd); optik-cpp/src/lib.rs:141-144 uses
+// UnitQuaternion::from_matrix, which also returns the nearest rotation for an already-orthonormal block.
+void pose8_from_colmajor4x4(const double* m, double* p) {
+  const double r00 = m[0], r10 = m[1], r20 = m[2], r01 = m[4], r11 = m[5], r21 = m[6], r02 = m[8], r12 = m[9], r22 = m[10];
+  double q[4];
+  const double tr = r00 + r11 + r22;
+  if (tr > 0) {
+    const double s = sqrt(tr + 1.0) * 2;
+    q[3] = 0.25 * s; q[0] = (r21 - r12) / s; q[1] = (r02 - r20) / s; q[2] = (r10 - r01) / s;
+  } else if (r00 > r11 && r00 > r22) {
+    const double s = sqrt(1.0 + r00 - r11 - r22) * 2;
+    q[3] = (r21 - r12) / s; q[0] = 0.25 * s; q[1] = (r01 + r10) / s; q[2] = (r02 + r20) / s;
+  } else if (r11 > r22) {
+    const double s = sqrt(1.0 + r11 - r00 - r22) * 2;
+    q[3] = (r02 - r20) / s; q[0] = (r01 + r10) / s; q[1] = 0.25 * s; q[2] = (r12 + r21) / s;
+  } else {
+    const double s = sqrt(1.0 + r22 - r00 - r11) * 2;
+    q[3] = (r10 - r01) / s; q[0] = (r02 + r20) / s; q[1] = (r12 + r21) / s; q[2] = 0.25 * s;
+  }
+  const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) p[i] = q[i] / nrm;
+  p[4] = m[12]; p[5] = m[13]; p[6] = m[14]; p[7] = 0;
+}
+void colmajor4x4_from_pose8(const double* p, double* m) {
+  const double x = p[0], y = p[1], z = p[2], w = p[3];
+  m[0] = 1 - 2 * (y * y + z * z); m[4] = 2 * (x * y - z * w);     m[8] = 2 * (x * z + y * w);      m[12] = p[4];
+  m[1] = 2 * (x * y + z * w);     m[5] = 1 - 2 * (x * x + z * z); m[9] = 2 * (y * z - x * w);      m[13] = p[5];
+  m[2] = 2 * (x * z - y * w);     m[6] = 2 * (y * z + x * w);     m[10] = 1 - 2 * (x * x + y * y); m[14] = p[6];
+  m[3] = 0; m[7] = 0; m[11] = 0; m[15] = 1;
+}
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cap = bytes;
+    return 0;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+struct optik_robot {
+  std::vector<optik::Joint> joints;  // articulated joints, then at most one fixed tip joint
+  int n = 0;                         // num_positions
+  bool kernel_ok = true;             // chain shape supported by the kernels
+  std::string why_not;
+  unsigned parallelism = 0;
+  int device = 0;
+  // lazily created GPU state
+  mutable std::mutex mu;
+  mutable bool gpu_ready = false;
+  mutable DevBuf chain_dev;
+  mutable uint32_t chain_bytes = 0;
+  mutable int sm_count = 0;
+  mutable int occ[3] = {0, 0, 0};  // resident blocks/SM for TILE 8,16,32
+  mutable DevBuf scratch;          // single-call scratch (ik / fk / jacobian), guarded by mu
+  mutable cudaStream_t stream = nullptr;
+  mutable void* pinned = nullptr;
+  mutable size_t pinned_cap = 0;
+
+  ~optik_robot() {
+    if (stream) cudaStreamDestroy(stream);
+    if (pinned) cudaFreeHost(pinned);
+  }
+  void finish_init() {
+    n = 0;
+    for (size_t i = 0; i < joints.size(); i++) {
+      if (joints[i].type != optik::FIXED) n++;
+      else if (i + 1 != joints.size()) { kernel_ok = false; why_not = "fixed joint in the middle of the chain"; }
+    }
+    if (n > OPTIK_MAX_DOF) { kernel_ok = false; why_not = "more than 32 articulated joints"; }
+  }
+  std::vector<double> flat_chain() const {
+    std::vector<double> c(joints.size() * OPTIK_CHAIN_STRIDE, 0.0);
+    for (size_t i = 0; i < joints.size(); i++) {
+      double* j = &c[i * OPTIK_CHAIN_STRIDE];
+      const optik::Joint& J = joints[i];
+      j[0] = J.origin.t[0]; j[1] = J.origin.t[1]; j[2] = J.origin.t[2]; j[3] = (double)J.type;
+      j[4] = J.origin.q[0]; j[5] = J.origin.q[1]; j[6] = J.origin.q[2]; j[7] = J.origin.q[3];
+      j[8] = J.axis[0]; j[9] = J.axis[1]; j[10] = J.axis[2];
+      j[12] = J.lower; j[13] = J.upper;
+    }
+    return c;
+  }
+  // device blob: n joint records (128 B each, with seed-sampling limits) + fixed tip pose8
+  int ensure_gpu() const {
+    if (gpu_ready) return 0;
+    if (!kernel_ok) return fail(OPTIK_ERR_UNSUPPORTED, "chain not supported by the GPU kernels: " + why_not);
+    CUDA_TRY(cudaSetDevice(device));
+    std::vector<double> blob((size_t)n * OPTIK_CHAIN_STRIDE + 8, 0.0);
+    const double PI = 3.14159265358979311600e+00;
+    int k = 0;
+    pose8_identity(&blob[(size_t)n * OPTIK_CHAIN_STRIDE]);
+    for (const optik::Joint& J : joints) {
+      if (J.type == optik::FIXED) {
+        double* t = &blob[(size_t)n * OPTIK_CHAIN_STRIDE];
+        t[0] = J.origin.q[0]; t[1] = J.origin.q[1]; t[2] = J.origin.q[2]; t[3] = J.origin.q[3];
+        t[4] = J.origin.t[0]; t[5] = J.origin.t[1]; t[6] = J.origin.t[2]; t[7] = 0;
+        continue;
+      }
+      double* j = &blob[(size_t)k * OPTIK_CHAIN_STRIDE];
+      j[0] = J.origin.t[0]; j[1] = J.origin.t[1]; j[2] = J.origin.t[2]; j[3] = (double)J.type;
+      j[4] = J.origin.q[0]; j[5] = J.origin.q[1]; j[6] = J.origin.q[2]; j[7] = J.origin.q[3];
+      j[8] = J.axis[0]; j[9] = J.axis[1]; j[10] = J.axis[2];
+      j[12] = J.lower; j[13] = J.upper;
+      const bool finite = std::isfinite(J.lower) && std::isfinite(J.upper);
+      j[14] = finite ? J.lower : -PI;  // infinite limits: the reference's uniform draw is undefined; we use [-pi, pi]
+      j[15] = finite ? J.upper : PI;
+      k++;
+    }
+    chain_bytes = (uint32_t)(blob.size() * sizeof(double));
+    if (chain_dev.reserve(chain_bytes)) return fail(OPTIK_ERR_CUDA, "cudaMalloc(chain) failed");
+    CUDA_TRY(cudaMemcpy(chain_dev.p, blob.data(), chain_bytes, cudaMemcpyHostToDevice));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    const int tiles[3] = {8, 16, 32};
+    for (int i = 0; i < 3; i++) CUDA_TRY(optik_solve_occupancy(tiles[i], &occ[i]));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    gpu_ready = true;
+    return 0;
+  }
+};
+
+namespace {
+
+optik_robot* robot_from_chain(std::vector<optik::Joint>&& joints) {
+  auto* r = new optik_robot();
+  r->joints = std::move(joints);
+  r->finish_init();
+  return r;
+}
+
+optik_robot* try_from_urdf_str(const char* urdf, const char* base, const char* ee) {
+  try {
+    if (!urdf || !base || !ee) throw std::runtime_error("null argument");
+    return robot_from_chain(optik::chain_from_urdf(urdf, base, ee, g_urdf_correct_fold));
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return nullptr;
+  }
+}
+
+struct Plan {
+  int tile, blocks, tiles_per_block, resident_tiles;
+};
+int choose_tile(int n, uint32_t want) {
+  if (want == 8 || want == 16 || want == 32) return (int)want >= n ? (int)want : 0;
+  return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+}
+Plan make_plan(const optik_robot* r, int tile, uint32_t blocks_req, unsigned long long njobs) {
+  Plan p;
+  p.tile = tile;
+  p.tiles_per_block = 128 / tile;
+  const int oi = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
+  const int per_sm = r->occ[oi] > 0 ? r->occ[oi] : 1;
+  const long long resident_blocks = (long long)r->sm_count * per_sm;  // one full wave: a multiple of the SM count
+  p.resident_tiles = (int)(resident_blocks * p.tiles_per_block);
+  long long need = (long long)((njobs + p.tiles_per_block - 1) / p.tiles_per_block);
+  long long b = blocks_req ? blocks_req : (need < resident_blocks ? need : resident_blocks);
+  if (b < 1) b = 1;
+  p.blocks = (int)b;
+  return p;
+}
+
+void fill_common(const optik_robot* r, const optik_solver_config* cfg, const double* ee_offset, uint32_t max_evals,
+                 SolveParams& P) {
+  P.chain = (const double*)r->chain_dev.p;
+  P.n = r->n;
+  P.chain_bytes = r->chain_bytes;
+  P.mode = cfg->solution_mode;
+  P.tol_f = cfg->tol_f;
+  P.tol_df_eff = cfg->tol_df > 0.0 ? cfg->tol_df : 1e-3 * cfg->tol_f;  // lib.rs:283-293
+  P.tol_df_user = cfg->tol_df;
+  P.tol_dx = cfg->tol_dx;
+  P.weighted = 0;
+  for (int i = 0; i < 3; i++) {
+    P.wl[i] = cfg->linear_weight[i];
+    P.wa[i] = cfg->angular_weight[i];
+    if (P.wl[i] != 1.0 || P.wa[i] != 1.0) P.weighted = 1;
+  }
+  P.max_evals = max_evals ? (int)max_evals : OPTIK_LM_MAX_EVALS;
+  P.lambda0 = OPTIK_LM_LAMBDA0; P.lambda_dec = OPTIK_LM_LAMBDA_DEC; P.lambda_inc = OPTIK_LM_LAMBDA_INC;
+  P.lambda_min = OPTIK_LM_LAMBDA_MIN; P.lambda_max = OPTIK_LM_LAMBDA_MAX;
+  P.stall_rel = OPTIK_LM_STALL_REL; P.stall_count = OPTIK_LM_STALL_COUNT;
+  seed_key_from_u64(RNG_SEED, P.key);
+  if (ee_offset) for (int i = 0; i < 8; i++) P.ee_offset[i] = ee_offset[i];
+  else pose8_identity(P.ee_offset);
+}
+
+bool config_valid(const optik_solver_config* c) {
+  return c && (c->solution_mode == OPTIK_MODE_QUALITY || c->solution_mode == OPTIK_MODE_SPEED);
+}
+
+// Device-side batched solve on `stream`; every pointer is device memory.  Stream-ordered scratch.
+int solve_device(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
+                 const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
+                 double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
+                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s) {
+  const int tile = choose_tile(r->n, o ? o->tile : 0);
+  if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 8, 16 or 32 and >= num_positions");
+  SolveParams P{};
+  fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
+  P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
+  P.max_ns = max_ns;
+  P.counters = (unsigned long long*)d_counters;
+  // chunks per target
+  Plan plan0 = make_plan(r, tile, o ? o->blocks : 0, ~0ull);
+  uint64_t C = o ? o->chunks : 0;
+  if (per_attempt_records) C = R;
+  if (C == 0) {
+    const uint64_t want = 2ull * (uint64_t)plan0.resident_tiles;
+    C = T >= want ? 1 : (want + T - 1) / T;
+  }
+  if (C > R) C = R;
+  if (C < 1) C = 1;
+  if (C > 0xffffffffull) return fail(OPTIK_ERR_INVALID, "too many chunks");
+  P.C = (uint32_t)C;
+  const unsigned long long njobs = T * C;
+  Plan plan = make_plan(r, tile, o ? o->blocks : 0, njobs);
+  const int n = r->n;
+  const bool direct = (C == 1) || per_attempt_records;  // candidate records ARE the outputs
+  // scratch: optional outputs the caller did not ask for + candidate arrays when a selection pass follows
+  size_t bytes = 0;
+  auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
+  const size_t off_q = direct ? 0 : carve(njobs * n * sizeof(double));
+  const size_t off_f = direct ? 0 : carve(njobs * sizeof(double));
+  const size_t off_st = direct ? 0 : carve(njobs * sizeof(int));
+  const size_t off_score = carve(njobs * sizeof(double));
+  const size_t off_rs = (direct && d_restart) ? 0 : carve(njobs * sizeof(unsigned long long));
+  const size_t off_ev = (direct && d_evals) ? 0 : carve(njobs * sizeof(int));
+  const bool use_found = (cfg->solution_mode == OPTIK_MODE_SPEED) && C > 1 && !per_attempt_records;
+  const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
+  char* scratch = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, s));
+  P.cand_q = direct ? d_q : (double*)(scratch + off_q);
+  P.cand_f = direct ? d_f : (double*)(scratch + off_f);
+  P.cand_status = direct ? d_status : (int*)(scratch + off_st);
+  P.cand_score = (double*)(scratch + off_score);
+  P.cand_restart = (direct && d_restart) ? (unsigned long long*)d_restart : (unsigned long long*)(scratch + off_rs);
+  P.cand_evals = (direct && d_evals) ? d_evals : (int*)(scratch + off_ev);
+  P.found = nullptr;
+  if (use_found) {
+    P.found = (unsigned long long*)(scratch + off_found);
+    CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
+  }
+  CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
+  if (!direct) {
+    if (T > 0x7fffffffull) return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
+    SelectParams S{};
+    S.T = T; S.C = P.C; S.n = n;
+    S.cand_q = P.cand_q; S.cand_f = P.cand_f; S.cand_score = P.cand_score; S.cand_restart = P.cand_restart;
+    S.cand_status = P.cand_status; S.cand_evals = P.cand_evals;
+    S.tol_f = cfg->tol_f; S.tol_df_user = cfg->tol_df; S.tol_dx = cfg->tol_dx;
+    S.q_out = d_q; S.f_out = d_f; S.status_out = d_status;
+    S.restart_out = (unsigned long long*)d_restart;  // optional
+    S.evals_out = d_evals;                            // optional
+    CUDA_TRY(optik_launch_select(&S, s));
+  }
+  CUDA_TRY(cudaFreeAsync(scratch, s));
+  return OPTIK_OK;
+}
+
+int check_seeds_host(const optik_robot* r, const double* x0, uint64_t T) {  // lib.rs:251-254
+  const int n = r->n;
+  for (uint64_t t = 0; t < T; t++) {
+    int k = 0;
+    for (const optik::Joint& J : r->joints) {
+      if (J.type == optik::FIXED) continue;
+      const double q = x0[t * n + k];
+      if (q < J.lower || q > J.upper) return fail(OPTIK_ERR_SEED_LIMITS, "seed joint position outside of joint limits");
+      k++;
+    }
+  }
+  return OPTIK_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* optik_last_error(void) { return g_last_error.c_str(); }
+void optik_set_urdf_correct_fold(int on) { g_urdf_correct_fold = on != 0; }
+
+optik_robot* optik_robot_try_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link) {
+  return try_from_urdf_str(urdf, base_link, ee_link);
+}
+optik_robot* optik_robot_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link) {
+  optik_robot* r = try_from_urdf_str(urdf, base_link, ee_link);
+  if (!r) panic(g_last_error);
+  return r;
+}
+optik_robot* optik_robot_from_urdf_file(const char* path, const char* base_link, const char* ee_link) {
+  if (!path) panic("null path");
+  std::ifstream f(path, std::ios::binary);
+  if (!f) panic("error parsing URDF file!: cannot open '" + std::string(path) + "'");
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return optik_robot_from_urdf_str(ss.str().c_str(), base_link, ee_link);
+}
+optik_robot* optik_robot_from_chain(const double* chain, unsigned int njoints) {
+  if (!chain || njoints == 0) { g_last_error = "kinematic chain is empty"; return nullptr; }
+  std::vector<optik::Joint> joints(njoints);
+  int nq = 0;
+  for (unsigned i = 0; i < njoints; i++) {
+    const double* j = chain + (size_t)i * OPTIK_CHAIN_STRIDE;
+    optik::Joint& J = joints[i];
+    J.type = (int)j[3];
+    if (J.type < 0 || J.type > 2) { g_last_error = "joint type not supported"; return nullptr; }
+    J.origin.t[0] = j[0]; J.origin.t[1] = j[1]; J.origin.t[2] = j[2];
+    J.origin.q[0] = j[4]; J.origin.q[1] = j[5]; J.origin.q[2] = j[6]; J.origin.q[3] = j[7];
+    J.axis[0] = j[8]; J.axis[1] = j[9]; J.axis[2] = j[10];
+    J.lower = j[12]; J.upper = j[13];
+    nq += (J.type != optik::FIXED);
+  }
+  if (nq == 0) { g_last_error = "kinematic chain is empty"; return nullptr; }
+  return robot_from_chain(std::move(joints));
+}
+void optik_robot_free(optik_robot* robot) { delete robot; }
+
+void optik_robot_set_parallelism(optik_robot* robot, unsigned int n) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  robot->parallelism = n;
+}
+unsigned int optik_robot_num_positions(const optik_robot* robot) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  return (unsigned)robot->n;
+}
+unsigned int optik_robot_num_joints(const optik_robot* robot) { return robot ? (unsigned)robot->joints.size() : 0; }
+int optik_robot_chain(const optik_robot* robot, double* out) {
+  if (!robot || !out) return fail(OPTIK_ERR_INVALID, "null argument");
+  std::vector<double> c = robot->flat_chain();
+  memcpy(out, c.data(), c.size() * sizeof(double));
+  return OPTIK_OK;
+}
+int optik_robot_set_device(optik_robot* robot, int device) {
+  if (!robot) return fail(OPTIK_ERR_INVALID, "null robot");
+  std::lock_guard<std::mutex> lk(robot->mu);
+  if (robot->gpu_ready && robot->device != device) return fail(OPTIK_ERR_INVALID, "device already initialised");
+  robot->device = device;
+  return OPTIK_OK;
+}
+int optik_status_is_success(const optik_solver_config* c, int st) {
+  if (!c) return 0;
+  return (c->tol_f >= 0.0 && st == OPTIK_STATUS_STOPVAL) || (c->tol_df >= 0.0 && st == OPTIK_STATUS_FTOL) ||
+         (c->tol_dx >= 0.0 && st == OPTIK_STATUS_XTOL);
+}
+
+double* optik_robot_joint_limits(const optik_robot* robot) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  double* out = (double*)malloc(sizeof(double) * 2 * robot->n);
+  int k = 0;
+  for (const optik::Joint& J : robot->joints) {
+    if (J.type == optik::FIXED) continue;
+    out[k] = J.lower;
+    out[robot->n + k] = J.upper;
+    k++;
+  }
+  return out;
+}
+double* optik_robot_random_configuration(const optik_robot* robot) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  static thread_local std::mt19937_64 rng{std::random_device{}()};  // rand::rng(): thread-local, OS-seeded
+  double* out = (double*)malloc(sizeof(double) * robot->n);
+  int k = 0;
+  for (const optik::Joint& J : robot->joints) {
+    if (J.type == optik::FIXED) continue;
+    if (!(std::isfinite(J.lower) && std::isfinite(J.upper))) panic("cannot sample a joint with infinite limits");
+    out[k++] = std::uniform_real_distribution<double>(J.lower, std::nextafter(J.upper, INFINITY))(rng);
+  }
+  return out;
+}
+
+void* optik_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_last_error = "cudaMallocHost failed"; return nullptr; }
+  return p;
+}
+void optik_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------- batched evaluator
+int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double* targets, int shared_target,
+                         uint64_t B, const double* linear_weight, const double* angular_weight,
+                         const double* ee_offset, int memory, double* ee_out, double* jac_out, double* f_out,
+                         double* grad_out, void* stream) {
+  if (!robot || !q) return fail(OPTIK_ERR_INVALID, "null argument");
+  if ((f_out || grad_out) && !targets) return fail(OPTIK_ERR_INVALID, "objective outputs need targets");
+  if (B == 0) return OPTIK_OK;
+  std::unique_lock<std::mutex> lk(robot->mu);
+  if (int rc = robot->ensure_gpu()) return rc;
+  CUDA_TRY(cudaSetDevice(robot->device));
+  const int n = robot->n;
+  if (optik_eval_smem_bytes(n) > 227 * 1024) return fail(OPTIK_ERR_UNSUPPORTED, "chain too long for the evaluator tile");
+  // device-pointer calls run on the caller's stream (NULL = the legacy default stream); host-pointer calls on ours
+  cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
+  if (memory == 1) lk.unlock();  // device-pointer calls only touch immutable robot state
+  EvalParams P{};
+  P.chain = (const double*)robot->chain_dev.p; P.n = n; P.chain_bytes = robot->chain_bytes;
+  P.B = B; P.target_stride = shared_target ? 0 : 8;
+  P.weighted = 0;
+  for (int i = 0; i < 3; i++) {
+    P.wl[i] = linear_weight ? linear_weight[i] : 1.0;
+    P.wa[i] = angular_weight ? angular_weight[i] : 1.0;
+    if (P.wl[i] != 1.0 || P.wa[i] != 1.0) P.weighted = 1;
+  }
+  if (ee_offset) for (int i = 0; i < 8; i++) P.ee_offset[i] = ee_offset[i];
+  else pose8_identity(P.ee_offset);
+  const uint64_t nblk = (B + 127) / 128;
+  const int blocks = (int)(nblk < (uint64_t)robot->sm_count * 8 ? nblk : (uint64_t)robot->sm_count * 8);
+  if (memory == 1) {
+    P.q = q; P.targets = targets; P.ee_out = ee_out; P.jac_out = jac_out; P.f_out = f_out; P.grad_out = grad_out;
+    CUDA_TRY(optik_launch_eval(&P, blocks, s));
+    return OPTIK_OK;
+  }
+  // host pointers: stage through stream-ordered device buffers
+  const uint64_t nt = shared_target ? 1 : B;
+  size_t bytes = 0;
+  auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
+  const size_t o_q = carve(B * n * 8), o_t = targets ? carve(nt * 64) : 0, o_ee = ee_out ? carve(B * 64) : 0,
+               o_j = jac_out ? carve(B * 6 * n * 8) : 0, o_f = f_out ? carve(B * 8) : 0, o_g = grad_out ? carve(B * n * 8) : 0;
+  char* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_q, q, B * n * 8, cudaMemcpyHostToDevice, s));
+  if (targets) CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, nt * 64, cudaMemcpyHostToDevice, s));
+  P.q = (double*)(d + o_q); P.targets = targets ? (double*)(d + o_t) : nullptr;
+  P.ee_out = ee_out ? (double*)(d + o_ee) : nullptr; P.jac_out = jac_out ? (double*)(d + o_j) : nullptr;
+  P.f_out = f_out ? (double*)(d + o_f) : nullptr; P.grad_out = grad_out ? (double*)(d + o_g) : nullptr;
+  CUDA_TRY(optik_launch_eval(&P, blocks, s));
+  if (ee_out) CUDA_TRY(cudaMemcpyAsync(ee_out, d + o_ee, B * 64, cudaMemcpyDeviceToHost, s));
+  if (jac_out) CUDA_TRY(cudaMemcpyAsync(jac_out, d + o_j, B * 6 * n * 8, cudaMemcpyDeviceToHost, s));
+  if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out, d + o_f, B * 8, cudaMemcpyDeviceToHost, s));
+  if (grad_out) CUDA_TRY(cudaMemcpyAsync(grad_out, d + o_g, B * n * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return OPTIK_OK;
+}
+
+double* optik_robot_fk(const optik_robot* robot, const double* x) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  double ee[8];
+  if (optik_gpu_eval_batch(robot, x, nullptr, 0, 1, nullptr, nullptr, nullptr, 0, ee, nullptr, nullptr, nullptr, nullptr))
+    panic("fk: " + g_last_error);
+  double* m = (double*)malloc(sizeof(double) * 16);
+  colmajor4x4_from_pose8(ee, m);
+  return m;
+}
+double* optik_robot_joint_jacobian(const optik_robot* robot, const double* x) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  for (const optik::Joint& J : robot->joints)
+    if (J.type == optik::PRISMATIC) panic("not yet implemented: prismatic joints not yet supported");  // kinematics.rs:185
+  double* jac = (double*)malloc(sizeof(double) * 6 * robot->n);
+  if (optik_gpu_eval_batch(robot, x, nullptr, 0, 1, nullptr, nullptr, nullptr, 0, nullptr, jac, nullptr, nullptr, nullptr))
+    panic("joint_jacobian: " + g_last_error);
+  return jac;
+}
+
+// ---------------------------------------------------------------- batched ik
+static int batch_common(const optik_robot* robot, const optik_solver_config* config, const optik_gpu_batch_opts* opts,
+                        const double* targets, const double* x0, uint64_t T, double* q_out, double* cost_out,
+                        int32_t* status_out, int32_t* evals_all, bool per_attempt, void* stream) {
+  if (!robot || !targets || !x0 || !q_out || !cost_out || !status_out) return fail(OPTIK_ERR_INVALID, "null argument");
+  if (!config_valid(config)) return fail(OPTIK_ERR_INVALID, "invalid solver config / solution_mode");
+  if (opts && opts->struct_size != sizeof(optik_gpu_batch_opts)) return fail(OPTIK_ERR_INVALID, "opts.struct_size mismatch");
+  if (T == 0) return OPTIK_OK;
+  uint64_t R = opts ? opts->restarts : 0;
+  if (R == 0) {
+    if (config->max_restarts == 0 || config->max_restarts > 0xffffffffull)
+      return fail(OPTIK_ERR_INVALID, "batched ik needs a finite restart budget (opts.restarts or config.max_restarts)");
+    R = config->max_restarts;
+  }
+  const uint64_t r_begin = opts ? opts->restart_begin : 0;
+  const int memory = opts ? opts->memory : 0;
+  std::unique_lock<std::mutex> lk(robot->mu);
+  if (int rc = robot->ensure_gpu()) return rc;
+  CUDA_TRY(cudaSetDevice(robot->device));
+  cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
+  const int n = robot->n;
+  const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(config->max_time * 1e9) : 0ull;
+  const uint64_t NO = per_attempt ? R : T;  // number of output records
+  if (memory == 1) {
+    lk.unlock();
+    // seeds outside the limits cannot be checked without a sync; they are clamped by the kernel (documented)
+    return solve_device(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
+                        opts ? opts->restart_out : nullptr, per_attempt ? evals_all : (opts ? opts->evals_out : nullptr),
+                        opts ? opts->counters : nullptr, max_ns, per_attempt, s);
+  }
+  if (int rc = check_seeds_host(robot, x0, T)) return rc;
+  size_t bytes = 0;
+  auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
+  const bool want_rs = opts && opts->restart_out, want_cnt = opts && opts->counters;
+  int32_t* evals_host = per_attempt ? evals_all : (opts ? opts->evals_out : nullptr);
+  const size_t o_t = carve(T * 64), o_x = carve(T * n * 8), o_q = carve(NO * n * 8), o_f = carve(NO * 8),
+               o_s = carve(NO * 4), o_r = want_rs ? carve(NO * 8) : 0, o_e = evals_host ? carve(NO * 4) : 0,
+               o_c = want_cnt ? carve(24) : 0;
+  char* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, T * 64, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_x, x0, T * n * 8, cudaMemcpyHostToDevice, s));
+  if (want_cnt) CUDA_TRY(cudaMemsetAsync(d + o_c, 0, 24, s));
+  int rc = solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
+                        (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
+                        evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
+                        per_attempt, s);
+  if (rc) { cudaFreeAsync(d, s); return rc; }
+  CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, NO * 4, cudaMemcpyDeviceToHost, s));
+  if (want_rs) CUDA_TRY(cudaMemcpyAsync(opts->restart_out, d + o_r, NO * 8, cudaMemcpyDeviceToHost, s));
+  if (evals_host) CUDA_TRY(cudaMemcpyAsync(evals_host, d + o_e, NO * 4, cudaMemcpyDeviceToHost, s));
+  uint64_t cnt[3] = {0, 0, 0};
+  if (want_cnt) CUDA_TRY(cudaMemcpyAsync(cnt, d + o_c, 24, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (want_cnt) for (int i = 0; i < 3; i++) opts->counters[i] += cnt[i];
+  return OPTIK_OK;
+}
+
+int optik_gpu_ik_batch(const optik_robot* robot, const optik_solver_config* config, const optik_gpu_batch_opts* opts,
+                       const double* targets, const double* x0, uint64_t T, double* q_out, double* cost_out,
+                       int32_t* status_out, void* stream) {
+  return batch_common(robot, config, opts, targets, x0, T, q_out, cost_out, status_out, nullptr, false, stream);
+}
+int optik_gpu_ik_attempts(const optik_robot* robot, const optik_solver_config* config,
+                          const optik_gpu_batch_opts* opts, const double* target, const double* x0, double* q_all,
+                          double* f_all, int32_t* status_all, int32_t* evals_all, void* stream) {
+  if (!evals_all) return fail(OPTIK_ERR_INVALID, "null argument");
+  return batch_common(robot, config, opts, target, x0, 1, q_all, f_all, status_all, evals_all, true, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- Robot::ik (single target), lib.rs:241-415
+// Returns 1 and fills q_out/cost_out when a restart converged, 0 for "no solution" (== None), <0 = -(error code).
+static int ik_single(const optik_robot* robot, const optik_solver_config* config, const double* tgt8, const double* x0,
+                     const double* ee_offset, double* q_out, double* cost_out) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int n = robot->n;
+  if (int rc = check_seeds_host(robot, x0, 1)) return -rc;
+  std::lock_guard<std::mutex> lk(robot->mu);
+  if (int rc = robot->ensure_gpu()) return -rc;
+  if (cudaSetDevice(robot->device) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t s = robot->stream;
+  const int tile = choose_tile(n, 0);
+  const Plan plan = make_plan(robot, tile, 0, ~0ull);
+  const uint64_t wave = (uint64_t)plan.resident_tiles;                                    // restarts per launch
+  const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
+  const size_t o_t = 0, o_x = 64, o_q = o_x + ((n * 8 + 255) & ~255), o_f = o_q + ((n * 8 + 255) & ~255), o_s = o_f + 256,
+               total = o_s + 256;
+  if (robot->scratch.reserve(total)) return -fail(OPTIK_ERR_CUDA, "cudaMalloc failed");
+  char* d = (char*)robot->scratch.p;
+  if (!robot->pinned) {
+    if (cudaMallocHost(&robot->pinned, 4096) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaMallocHost failed");
+    robot->pinned_cap = 4096;
+  }
+  double* h = (double*)robot->pinned;  // [0..7] target, [8..8+n) x0, [64..64+n) q, [100] f, [101] status
+  memcpy(h, tgt8, 64);
+  memcpy(h + 8, x0, n * 8);
+  if (cudaMemcpyAsync(d + o_t, h, 64, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(d + o_x, h + 8, n * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return -fail(OPTIK_ERR_CUDA, "H2D copy failed");
+  optik_gpu_batch_opts o{};
+  o.struct_size = sizeof(o);
+  o.memory = 1;
+  o.ee_offset = ee_offset;
+  bool have_best = false;
+  double best_score = 0;
+  uint64_t done = 0;
+  while (done < max_restarts) {
+    // budget check between waves (lib.rs:260-264, 393-394); inside a wave the kernel checks the same deadline
+    double remaining = 0;
+    if (config->max_time > 0.0) {
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+      remaining = config->max_time - el;
+      if (remaining <= 0) break;
+    }
+    const uint64_t R = (max_restarts - done) < wave ? (max_restarts - done) : wave;
+    const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(remaining * 1e9) + 1 : 0ull;
+    if (int rc = solve_device(robot, config, &o, (double*)(d + o_t), (double*)(d + o_x), 1, done, R, (double*)(d + o_q),
+                              (double*)(d + o_f), (int32_t*)(d + o_s), nullptr, nullptr, nullptr, max_ns, false, s))
+      return -rc;
+    if (cudaMemcpyAsync(h + 64, d + o_q, n * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(h + 100, d + o_f, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(h + 101, d + o_s, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return -fail(OPTIK_ERR_CUDA, std::string("ik: ") + cudaGetErrorString(cudaGetLastError()));
+    done += R;
+    int32_t st;
+    memcpy(&st, h + 101, 4);
+    if (optik_status_is_success(config, st)) {
+      double score = 0;
+      for (int i = 0; i < n; i++) score += (h[64 + i] - x0[i]) * (h[64 + i] - x0[i]);
+      if (!have_best || score < best_score) {
+        have_best = true; best_score = score;
+        memcpy(q_out, h + 64, n * 8);
+        *cost_out = h[100];
+      }
+      if (config->solution_mode == OPTIK_MODE_SPEED) break;  // the first wave with a success holds the lowest index
+    }
+  }
+  return have_best ? 1 : 0;
+}
+
+extern "C" int optik_robot_ik_ex(const optik_robot* robot, const optik_solver_config* config, const double* target_pose8,
+                                 const double* x0, const double* ee_offset_pose8, double* q_out, double* cost_out) {
+  if (!robot || !config || !target_pose8 || !x0 || !q_out || !cost_out) return -fail(OPTIK_ERR_INVALID, "null argument");
+  if (!config_valid(config)) return -fail(OPTIK_ERR_INVALID, "invalid solution mode");
+  return ik_single(robot, config, target_pose8, x0, ee_offset_pose8, q_out, cost_out);
+}
+
+extern "C" double* optik_robot_ik(const optik_robot* robot, const optik_solver_config* config, const double* target,
+                                  const double* x0) {
+  if (!robot || !config || !target || !x0) panic("called `Option::unwrap()` on a `None` value (null argument)");
+  if (!config_valid(config)) panic("invalid solution mode");
+  double tgt8[8], cost = 0;
+  pose8_from_colmajor4x4(target, tgt8);
+  double* out = (double*)malloc(sizeof(double) * robot->n);
+  const int rc = ik_single(robot, config, tgt8, x0, nullptr, out, &cost);
+  if (rc == 1) return out;
+  free(out);
+  if (rc < 0) panic(g_last_error);  // e.g. "seed joint position outside of joint limits" (lib.rs:251-254)
+  return nullptr;
+}
+
+extern "C" double* optik_robot_diff_ik(const optik_robot* robot, const double*, const double*, const double*) {
+  if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
+  static bool warned = false;
+  if (!warned) { warned = true; fprintf(stderr, "optik_b200: diff_ik is outside the scope of this build (returns no solution)\n"); }
+  return nullptr;
+}

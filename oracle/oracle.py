@@ -137,3 +137,87 @@ def se3_right_jacobian(p8):
     U = np.zeros(36)
     lib().oracle_se3_right_jacobian(_p(_d(p8)), _p(U))
     return U  # column-major
+
+
+# ---------------------------------------------------------------- solver twin
+ST_NAMES = {0: "none", 1: "stopval", 2: "ftol", 3: "xtol", 4: "itercap", 5: "stuck", 6: "nan", 7: "skipped"}
+
+
+class TwinParams(C.Structure):
+    _fields_ = [("tol_f", C.c_double), ("tol_df_eff", C.c_double), ("tol_df_user", C.c_double), ("tol_dx", C.c_double),
+                ("wl", C.c_double * 3), ("wa", C.c_double * 3), ("weighted", C.c_int), ("max_evals", C.c_int),
+                ("lambda0", C.c_double), ("lambda_dec", C.c_double), ("lambda_inc", C.c_double),
+                ("lambda_min", C.c_double), ("lambda_max", C.c_double),
+                ("stall_rel", C.c_double), ("stall_count", C.c_int)]
+
+
+# defaults of the kernel's LM iteration (DESIGN.md "Solver"); keep in sync with optik_b200/csrc/solver_params.h
+LM_DEFAULTS = dict(max_evals=64, lambda0=1e-1, lambda_dec=0.3, lambda_inc=10.0, lambda_min=1e-9, lambda_max=1e6,
+                   stall_rel=1e-2, stall_count=3)
+
+
+def twin_params(tol_f=1e-6, tol_df=-1.0, tol_dx=-1.0, wl=(1, 1, 1), wa=(1, 1, 1), **lm):
+    """SolverConfig -> kernel parameters, as crates/optik/src/lib.rs:283-293 derives them."""
+    d = dict(LM_DEFAULTS)
+    d.update(lm)
+    p = TwinParams()
+    p.tol_f = tol_f
+    p.tol_df_eff = tol_df if tol_df > 0.0 else 1e-3 * tol_f
+    p.tol_df_user = tol_df
+    p.tol_dx = tol_dx
+    p.wl[:] = list(wl)
+    p.wa[:] = list(wa)
+    p.weighted = int(any(float(x) != 1.0 for x in list(wl) + list(wa)))
+    for k, v in d.items():
+        setattr(p, k, v)
+    return p
+
+
+def twin_eval(chain, q, target, params=None, ee_offset=None):
+    params = params or twin_params()
+    ee = np.zeros(8)
+    f = C.c_double()
+    r = np.zeros(6)
+    Jr = np.zeros((chain.n, 6))
+    g = np.zeros(chain.n)
+    rc = lib().twin_eval_c(_p(chain.arr), chain.njoints, _p(None if ee_offset is None else _d(ee_offset)),
+                           C.byref(params), _p(_d(target)), _p(_d(q)), _p(ee), C.byref(f), _p(r), _p(Jr), _p(g))
+    assert rc == 0, rc
+    return dict(ee=ee, f=f.value, r=r, Jr=Jr, grad=g)
+
+
+def twin_attempts(chain, target, x0, r_begin, r_end, params=None, ee_offset=None):
+    """Per-restart records for restarts [r_begin, r_end): q (R x n), f, status, evals."""
+    params = params or twin_params()
+    R = int(r_end - r_begin)
+    q = np.zeros((R, chain.n))
+    f = np.zeros(R)
+    st = np.zeros(R, dtype=np.int32)
+    ev = np.zeros(R, dtype=np.int32)
+    lib().twin_attempts_c.argtypes = [dp, C.c_int, dp, C.POINTER(TwinParams), dp, dp, C.c_uint64, C.c_uint64, dp, dp,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = lib().twin_attempts_c(_p(chain.arr), chain.njoints, _p(None if ee_offset is None else _d(ee_offset)),
+                               C.byref(params), _p(_d(target)), _p(_d(x0)), int(r_begin), int(r_end), _p(q), _p(f),
+                               st.ctypes.data_as(C.POINTER(C.c_int)), ev.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0, rc
+    return q, f, st, ev
+
+
+def twin_ik(chain, target, x0, r_begin, r_end, mode="speed", params=None, ee_offset=None):
+    """Reference selection semantics (lib.rs:397-413, single-threaded order) over the twin's attempts.
+
+    Returns dict(found, q, f, status, restart).  Speed: lowest-index converged restart; Quality: arg-min
+    ||q - x0||^2 (ties -> lower index) over all converged restarts in [r_begin, r_end)."""
+    params = params or twin_params()
+    n = chain.n
+    q = np.zeros(n)
+    f = C.c_double()
+    st = C.c_int()
+    rs = C.c_uint64()
+    lib().twin_ik_c.argtypes = [dp, C.c_int, dp, C.POINTER(TwinParams), dp, dp, C.c_uint64, C.c_uint64, C.c_int, dp,
+                                C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    found = lib().twin_ik_c(_p(chain.arr), chain.njoints, _p(None if ee_offset is None else _d(ee_offset)),
+                            C.byref(params), _p(_d(target)), _p(_d(x0)), int(r_begin), int(r_end),
+                            2 if mode == "speed" else 1, _p(q), C.byref(f), C.byref(st), C.byref(rs))
+    assert found >= 0, found
+    return dict(found=bool(found), q=q, f=f.value, status=st.value, restart=rs.value)

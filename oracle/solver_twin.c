@@ -1,0 +1,384 @@
+/*
+ * solver_twin.c -- CPU ORACLE, TEST INFRASTRUCTURE ONLY.
+ *
+ * fp64 twin of the CUDA solve kernel (optik_b200/csrc/solve_kernel.cu): the
+ * same algorithm, the same seeds, the same sequence of IEEE-754 operations
+ * (see twin_math.h), restated in plain C with the tile's lanes written as
+ * loops.  It checks GPU<->CPU parity per restart seed (status, iteration
+ * count, solution), which is where "identical success set under fixed RNG"
+ * is checkable.
+ *
+ * What it stands in for in the reference: the per-restart NLopt SLSQP solve
+ * and its stop rules, crates/optik/src/lib.rs:302-391 (stopval = tol_f :345,
+ * ftol_abs = tol_df_eff :283-293,:346, xtol_abs = tol_dx :347, bounds
+ * :348-349, success classification :376-379).  The inner optimiser is
+ * replaced BY DESIGN (north star) with a bound-projected Levenberg-Marquardt
+ * iteration in dual (6x6) form, so per-seed trajectories are "parity
+ * unpinned" against NLopt; the evaluator underneath is checked against
+ * optik_oracle.c (which is pinned to the reference's golden vectors).
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "twin_math.h"
+
+#define CHAIN_STRIDE 16
+#define MAX_DOF 32
+
+enum { /* attempt status; mirrored by optik_b200/csrc/solve_kernel.cu */
+  ST_NONE = 0,
+  ST_STOPVAL = 1,   /* f < tol_f                 (NLopt StopValReached) */
+  ST_FTOL = 2,      /* accepted |df| < tol_df    (NLopt FtolReached)    */
+  ST_XTOL = 3,      /* accepted max|dx| < tol_dx (NLopt XtolReached)    */
+  ST_ITERCAP = 4,   /* evaluation cap (no reference analogue)          */
+  ST_STUCK = 5,     /* damping exceeded lambda_max: no descent step     */
+  ST_NAN = 6,
+  ST_SKIPPED = 7    /* not run: timeout / Speed-mode early exit         */
+};
+
+typedef struct {
+  double tol_f, tol_df_eff, tol_df_user, tol_dx;
+  double wl[3], wa[3];
+  int weighted, max_evals;
+  double lambda0, lambda_dec, lambda_inc, lambda_min, lambda_max;
+  double stall_rel; /* accepted step with df < stall_rel*f counts as "slow" */
+  int stall_count;  /* this many consecutive slow steps => ST_STUCK */
+} twin_params;
+
+typedef struct {
+  int n;
+  int type[MAX_DOF];
+  v3 ot[MAX_DOF], ax[MAX_DOF];
+  qt oq[MAX_DOF];
+  double lb[MAX_DOF], ub[MAX_DOF], slb[MAX_DOF], sub[MAX_DOF]; /* s*: seed sampling range */
+  se3t tip;
+} twin_chain;
+
+typedef struct {
+  double f;
+  double r[6];
+  double Jr[MAX_DOF][6];
+  se3t ee;
+} twin_eval;
+
+static se3t se3_from_pose8(const double* p) {
+  se3t r;
+  r.q.x = p[0]; r.q.y = p[1]; r.q.z = p[2]; r.q.w = p[3];
+  r.t = v3_make(p[4], p[5], p[6]);
+  return r;
+}
+
+/* flat chain (articulated joints followed by at most one fixed tip joint) -> twin_chain */
+int twin_chain_init(twin_chain* c, const double* chain, int njoints, const double* ee_offset) {
+  const double PI = 3.14159265358979311600e+00;
+  static const double ID[8] = {0, 0, 0, 1, 0, 0, 0, 0};
+  int n = 0;
+  se3t fixed = se3_from_pose8(ID);
+  for (int i = 0; i < njoints; i++) {
+    const double* j = chain + CHAIN_STRIDE * i;
+    int type = (int)j[3];
+    if (type == 2) {
+      if (i != njoints - 1) return -1;
+      double p[8] = {j[4], j[5], j[6], j[7], j[0], j[1], j[2], 0};
+      fixed = se3_from_pose8(p);
+      continue;
+    }
+    if (n >= MAX_DOF) return -2;
+    c->type[n] = type;
+    c->ot[n] = v3_make(j[0], j[1], j[2]);
+    c->oq[n].x = j[4]; c->oq[n].y = j[5]; c->oq[n].z = j[6]; c->oq[n].w = j[7];
+    c->ax[n] = v3_make(j[8], j[9], j[10]);
+    c->lb[n] = j[12]; c->ub[n] = j[13];
+    int finite = isfinite(j[12]) && isfinite(j[13]);
+    c->slb[n] = finite ? j[12] : -PI;
+    c->sub[n] = finite ? j[13] : PI;
+    n++;
+  }
+  c->n = n;
+  c->tip = se3_mul(fixed, se3_from_pose8(ee_offset ? ee_offset : ID));
+  return 0;
+}
+
+static inline double dot6(const double* a, const double* b) {
+  return fma(a[0], b[0], fma(a[1], b[1], fma(a[2], b[2], fma(a[3], b[3], fma(a[4], b[4], a[5] * b[5])))));
+}
+static inline v3 weight3(qt tq, const double w[3], v3 u) {
+  v3 a = qt_rot(tq, u);
+  a = v3_make(a.x * w[0], a.y * w[1], a.z * w[2]);
+  return qt_rot_inv(tq, a);
+}
+
+/* One evaluation: FK scan, body Jacobian, se(3) log error, weighted residual r,
+ * weighted task Jacobian Jr = W * Jlog6(X) * J_body.
+ * (kinematics.rs:123-196, math.rs:40-203, objective.rs:7-110 -- restated.) */
+void twin_evaluate(const twin_chain* c, const twin_params* P, se3t tgt, const double* q, twin_eval* E) {
+  int n = c->n;
+  se3t T[MAX_DOF], Tn[MAX_DOF];
+  for (int j = 0; j < n; j++) { /* lane j: local transform origin_j * motion_j(q_j) */
+    if (c->type[j] == 0) {
+      double s, cs;
+      tw_sincos(0.5 * q[j], &s, &cs);
+      qt qa = {c->ax[j].x * s, c->ax[j].y * s, c->ax[j].z * s, cs};
+      T[j].q = qt_mul(c->oq[j], qa);
+      T[j].t = c->ot[j];
+    } else {
+      T[j].q = c->oq[j];
+      T[j].t = v3_add(c->ot[j], qt_rot(c->oq[j], v3_scale(c->ax[j], q[j])));
+    }
+  }
+  for (int d = 1; d < n; d <<= 1) { /* Kogge-Stone inclusive scan over lanes */
+    for (int j = 0; j < n; j++) Tn[j] = (j >= d) ? se3_mul(T[j - d], T[j]) : T[j];
+    memcpy(T, Tn, sizeof(se3t) * n);
+  }
+  se3t ee = se3_mul(T[n - 1], c->tip);
+  E->ee = ee;
+  /* pose error X = T_tgt^-1 * T_ee */
+  qt xq = qt_mul(qt_conj(tgt.q), ee.q);
+  v3 xt = qt_rot_inv(tgt.q, v3_sub(ee.t, tgt.t));
+  /* so3 log + scalar coefficients (half-angle identities; Taylor below theta^2 <= 1e-6) */
+  double qw = xq.w;
+  v3 v = v3_make(xq.x, xq.y, xq.z);
+  if (!(qw >= 0.0)) { qw = -qw; v = v3_neg(v); }
+  double vn2 = v3_dot(v, v), k, th2, ce, bq;
+  if (vn2 > 1e-6) {
+    double vn = sqrt(vn2);
+    double half = tw_atan2_pos(vn, qw);
+    double inv_vn = 1.0 / vn, inv_half = 1.0 / half;
+    k = half * inv_vn;                       /* atan2(|v|,w)/|v| */
+    double p = k * qw;                       /* (theta/2)/tan(theta/2) */
+    double it2 = 0.25 * (inv_half * inv_half); /* 1/theta^2 */
+    th2 = 4.0 * (half * half);
+    ce = (1.0 - p) * it2;                    /* coefficient of hat(w)^2 in V^-1, J and a_q of Q */
+    double a = (vn * qw) * inv_half;         /* sin(theta)/theta */
+    bq = fma((1.0 + a) * it2, 0.25 * (inv_vn * inv_vn), -2.0 * (it2 * it2));
+  } else {
+    double iw = 1.0 / qw, iw2 = iw * iw;
+    k = iw * fma(vn2 * iw2, fma(vn2 * iw2, 0.2, -1.0 / 3.0), 1.0);
+    th2 = 4.0 * ((k * k) * vn2);
+    ce = fma(th2, fma(th2, 1.0 / 30240.0, 1.0 / 720.0), 1.0 / 12.0);
+    bq = fma(th2, 1.0 / 7560.0, 1.0 / 360.0);
+  }
+  v3 w = v3_scale(v, k + k);
+  /* e = [V^-1 t ; w],  V^-1 u = u - 1/2 w x u + ce w x (w x u) */
+  v3 wxt = v3_cross(w, xt);
+  v3 elin = v3_axpy(ce, v3_cross(w, wxt), v3_axpy(-0.5, wxt, xt));
+  v3 rl = elin, ra = w;
+  if (P->weighted) { rl = weight3(tgt.q, P->wl, elin); ra = weight3(tgt.q, P->wa, w); }
+  E->r[0] = rl.x; E->r[1] = rl.y; E->r[2] = rl.z; E->r[3] = ra.x; E->r[4] = ra.y; E->r[5] = ra.z;
+  E->f = dot6(E->r, E->r);
+  /* Q = C*J scalars */
+  double d = v3_dot(w, xt);
+  double kc = fma(th2, bq, ce + ce);
+  v3 cv = v3_axpy(bq * d, w, v3_scale(xt, -kc)); /* b d w - (theta^2 b + 2a) t */
+  double da = d * ce;
+  for (int j = 0; j < n; j++) { /* lane j: body Jacobian column -> task column */
+    v3 lin, ang;
+    v3 axw = qt_rot(T[j].q, c->ax[j]);
+    if (c->type[j] == 0) {
+      v3 lw = v3_cross(axw, v3_sub(ee.t, T[j].t));
+      lin = qt_rot_inv(ee.q, lw);
+      ang = qt_rot_inv(ee.q, axw);
+    } else {
+      lin = qt_rot_inv(ee.q, axw);
+      ang = v3_make(0, 0, 0);
+    }
+    /* J u = u + 1/2 w x u + ce w x (w x u) */
+    v3 wxa = v3_cross(w, ang);
+    v3 ja = v3_axpy(ce, v3_cross(w, wxa), v3_axpy(0.5, wxa, ang));
+    v3 wxl = v3_cross(w, lin);
+    v3 jl = v3_axpy(ce, v3_cross(w, wxl), v3_axpy(0.5, wxl, lin));
+    /* C u = 1/2 t x u + cv (w.u) + ce w (t.u) + d ce u */
+    double wu = v3_dot(w, ja), tu = v3_dot(xt, ja);
+    v3 cu = v3_axpy(da, ja, v3_axpy(ce * tu, w, v3_axpy(wu, cv, v3_scale(v3_cross(xt, ja), 0.5))));
+    v3 top = v3_add(jl, cu), bot = ja;
+    if (P->weighted) { top = weight3(tgt.q, P->wl, top); bot = weight3(tgt.q, P->wa, bot); }
+    E->Jr[j][0] = top.x; E->Jr[j][1] = top.y; E->Jr[j][2] = top.z;
+    E->Jr[j][3] = bot.x; E->Jr[j][4] = bot.y; E->Jr[j][5] = bot.z;
+  }
+}
+
+/* xor-butterfly all-reduce over the tile (lanes >= n hold 0): pairwise tree, low strides first */
+static double tree_sum(const double* x, int n) {
+  double b[MAX_DOF];
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = 0; i < m; i++) b[i] = i < n ? x[i] : 0.0;
+  for (int s = 1; s < m; s <<= 1)
+    for (int i = 0; i < m; i += 2 * s) b[i] = b[i] + b[i + s];
+  return b[0];
+}
+
+/* LDL^T solve of the SPD 6x6 system A y = r (A symmetric, lower triangle used) */
+static void ldl6_solve(double A[6][6], const double* r, double* y) {
+  double L[6][6], D[6], inv[6];
+  for (int j = 0; j < 6; j++) {
+    double dj = A[j][j];
+    for (int k = 0; k < j; k++) dj = fma(-(L[j][k] * L[j][k]), D[k], dj);
+    D[j] = dj;
+    inv[j] = 1.0 / dj;
+    for (int i = j + 1; i < 6; i++) {
+      double s = A[i][j];
+      for (int k = 0; k < j; k++) s = fma(-(L[i][k] * L[j][k]), D[k], s);
+      L[i][j] = s * inv[j];
+    }
+  }
+  double z[6];
+  for (int i = 0; i < 6; i++) {
+    double s = r[i];
+    for (int k = 0; k < i; k++) s = fma(-L[i][k], z[k], s);
+    z[i] = s;
+  }
+  for (int i = 5; i >= 0; i--) {
+    double s = z[i] * inv[i];
+    for (int k = i + 1; k < 6; k++) s = fma(-L[k][i], y[k], s);
+    y[i] = s;
+  }
+}
+
+double* twin_trace = 0; /* debug: if set, receives (f_trial, lambda, accept) per evaluation */
+int twin_trace_cap = 0;
+void twin_set_trace(double* buf, int cap) { twin_trace = buf; twin_trace_cap = cap; }
+
+/* One restart attempt from q_init. Returns status; q_out/f_out = last trial point on exit. */
+int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const double* q_init, double* q_out,
+                 double* f_out, int* evals_out) {
+  int n = c->n, evals = 0, have_cur = 0, status = ST_NONE, slow = 0;
+  double qc[MAX_DOF], qt_[MAX_DOF], lambda = P->lambda0;
+  twin_eval Ec, Et;
+  Ec.f = 0;
+  for (int j = 0; j < n; j++) qt_[j] = fmin(fmax(q_init[j], c->lb[j]), c->ub[j]);
+  for (;;) {
+    twin_evaluate(c, P, tgt, qt_, &Et);
+    evals++;
+    int accept = 0;
+    if (Et.f != Et.f) status = ST_NAN;
+    else if (Et.f < P->tol_f) status = ST_STOPVAL;
+    else if (!have_cur) accept = 1;
+    else if (Et.f < Ec.f) {
+      accept = 1;
+      double df = Ec.f - Et.f, dx = 0;
+      for (int j = 0; j < n; j++) dx = fmax(dx, fabs(qt_[j] - qc[j]));
+      if (df < P->tol_df_eff) status = ST_FTOL;
+      else if (P->tol_dx > 0.0 && dx < P->tol_dx) status = ST_XTOL;
+      slow = (df < P->stall_rel * Ec.f) ? slow + 1 : 0;
+      if (status == ST_NONE && slow >= P->stall_count) status = ST_STUCK;
+      lambda = fmax(lambda * P->lambda_dec, P->lambda_min);
+    } else {
+      lambda = lambda * P->lambda_inc;
+      if (lambda > P->lambda_max) status = ST_STUCK;
+    }
+    if (twin_trace && evals <= twin_trace_cap) {
+      twin_trace[3 * (evals - 1)] = Et.f; twin_trace[3 * (evals - 1) + 1] = lambda; twin_trace[3 * (evals - 1) + 2] = accept;
+    }
+    if (status == ST_NONE && evals >= P->max_evals) status = ST_ITERCAP;
+    if (status != ST_NONE) break;
+    if (accept) { memcpy(qc, qt_, sizeof(double) * n); Ec = Et; have_cur = 1; }
+    /* step from the current point */
+    double m[MAX_DOF], A[6][6], y[6], tmp[MAX_DOF];
+    for (int j = 0; j < n; j++) {
+      double g = dot6(Ec.r, Ec.Jr[j]);
+      int pinned = (qc[j] <= c->lb[j] && g > 0.0) || (qc[j] >= c->ub[j] && g < 0.0);
+      m[j] = pinned ? 0.0 : 1.0;
+    }
+    for (int a = 0; a < 6; a++)
+      for (int b = 0; b <= a; b++) {
+        for (int j = 0; j < n; j++) tmp[j] = m[j] * (Ec.Jr[j][a] * Ec.Jr[j][b]);
+        A[a][b] = tree_sum(tmp, n);
+      }
+    for (int a = 0; a < 6; a++) A[a][a] = A[a][a] + lambda;
+    ldl6_solve(A, Ec.r, y);
+    for (int j = 0; j < n; j++) {
+      double dq = -(m[j] * dot6(Ec.Jr[j], y));
+      qt_[j] = fmin(fmax(qc[j] + dq, c->lb[j]), c->ub[j]);
+    }
+  }
+  memcpy(q_out, qt_, sizeof(double) * n);
+  *f_out = Et.f;
+  *evals_out = evals;
+  return status;
+}
+
+int twin_status_success(const twin_params* P, int status) { /* lib.rs:376-379 */
+  return (P->tol_f >= 0.0 && status == ST_STOPVAL) || (P->tol_df_user >= 0.0 && status == ST_FTOL) ||
+         (P->tol_dx >= 0.0 && status == ST_XTOL);
+}
+
+/* -------- entry points for ctypes -------- */
+void oracle_restart_seed(uint64_t restart, const double* lb, const double* ub, int n, double* q);
+
+/* evaluate with the twin arithmetic: outputs ee pose8, f, r[6], Jr (n x 6 row-major), grad[n] = 2 r^T Jr */
+int twin_eval_c(const double* chain, int njoints, const double* ee_offset, const twin_params* P, const double* target,
+                const double* q, double* ee8, double* f, double* r6, double* Jr, double* grad) {
+  twin_chain c;
+  int rc = twin_chain_init(&c, chain, njoints, ee_offset);
+  if (rc) return rc;
+  twin_eval E;
+  twin_evaluate(&c, P, se3_from_pose8(target), q, &E);
+  ee8[0] = E.ee.q.x; ee8[1] = E.ee.q.y; ee8[2] = E.ee.q.z; ee8[3] = E.ee.q.w;
+  ee8[4] = E.ee.t.x; ee8[5] = E.ee.t.y; ee8[6] = E.ee.t.z; ee8[7] = 0;
+  *f = E.f;
+  memcpy(r6, E.r, sizeof(E.r));
+  for (int j = 0; j < c.n; j++) {
+    memcpy(Jr + 6 * j, E.Jr[j], 6 * sizeof(double));
+    double g = dot6(E.r, E.Jr[j]);
+    grad[j] = g + g;
+  }
+  return 0;
+}
+
+/* Run restarts [r_begin, r_end) (restart 0 = x0, i>=1 = ChaCha8 stream i) for one target and record each attempt.
+ * q_all: (r_end-r_begin) x n, f_all, status_all, evals_all: per attempt. */
+int twin_attempts_c(const double* chain, int njoints, const double* ee_offset, const twin_params* P,
+                    const double* target, const double* x0, uint64_t r_begin, uint64_t r_end, double* q_all,
+                    double* f_all, int* status_all, int* evals_all) {
+  twin_chain c;
+  int rc = twin_chain_init(&c, chain, njoints, ee_offset);
+  if (rc) return rc;
+  se3t tgt = se3_from_pose8(target);
+  for (uint64_t r = r_begin; r < r_end; r++) {
+    double qi[MAX_DOF];
+    if (r == 0) memcpy(qi, x0, sizeof(double) * c.n);
+    else oracle_restart_seed(r, c.slb, c.sub, c.n, qi);
+    size_t o = (size_t)(r - r_begin);
+    status_all[o] = twin_attempt(&c, P, tgt, qi, q_all + o * c.n, f_all + o, evals_all + o);
+  }
+  return 0;
+}
+
+/* Robot::ik selection semantics in single-thread order (lib.rs:397-413) over restarts [r_begin, r_end).
+ * mode 2 = Speed: first converged restart.  mode 1 = Quality: arg-min ||q-x0||^2, ties -> lower index.
+ * Returns 1 if a restart converged (outputs describe it), else 0 (outputs describe the first attempt). */
+int twin_ik_c(const double* chain, int njoints, const double* ee_offset, const twin_params* P, const double* target,
+              const double* x0, uint64_t r_begin, uint64_t r_end, int mode, double* q_out, double* f_out,
+              int* status_out, uint64_t* restart_out) {
+  twin_chain c;
+  int rc = twin_chain_init(&c, chain, njoints, ee_offset);
+  if (rc) return rc;
+  se3t tgt = se3_from_pose8(target);
+  int have = 0, first = 1;
+  double best_score = 0;
+  for (uint64_t r = r_begin; r < r_end; r++) {
+    double qi[MAX_DOF], q[MAX_DOF], f, d2[MAX_DOF];
+    int evals;
+    if (r == 0) memcpy(qi, x0, sizeof(double) * c.n);
+    else oracle_restart_seed(r, c.slb, c.sub, c.n, qi);
+    int st = twin_attempt(&c, P, tgt, qi, q, &f, &evals);
+    int ok = twin_status_success(P, st);
+    if (ok) {
+      double score = 0.0;
+      if (mode == 1) {
+        for (int j = 0; j < c.n; j++) { double d = q[j] - x0[j]; d2[j] = d * d; }
+        score = tree_sum(d2, c.n);
+      }
+      if (!have || score < best_score) {
+        have = 1; best_score = score;
+        memcpy(q_out, q, sizeof(double) * c.n); *f_out = f; *status_out = st; *restart_out = r;
+      }
+      if (mode == 2) break;
+    } else if (!have && first) {
+      memcpy(q_out, q, sizeof(double) * c.n); *f_out = f; *status_out = st; *restart_out = r;
+    }
+    first = 0;
+  }
+  return have;
+}

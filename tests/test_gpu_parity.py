@@ -1,0 +1,277 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (north star): evaluator vs the golden-pinned fp64 oracle <= 1e-12 relative (fp64 arithmetic, different but
+equivalent formulas); solver vs its fp64 CPU twin: identical status / evaluation count per restart seed and
+solutions within 1e-6 rad (in practice bit-identical, which is asserted separately so a regression is visible).
+"""
+import numpy as np
+import pytest
+
+import optik_b200 as ob
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RAD_TOL = 1e-6  # north star: <= 1e-6 rad on converged seeds
+
+
+def robot_and_chain(name):
+    r = ob.Robot.named(name)
+    return r, O.Chain(r.chain())
+
+
+def targets_for(ch, rng, T):
+    out = np.zeros((T, 8))
+    for t in range(T):
+        out[t] = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    return out
+
+
+# ------------------------------------------------------------------ evaluator
+def test_fk_against_reference_golden(golden):  # tests/test_fk.rs:13-26 through the CUDA evaluator
+    r, _ = robot_and_chain("ur3e")
+    q = np.array(golden["fk_inputs"])
+    ee = r.eval_batch(q, want=("ee",))["ee"]
+    ref = np.array(golden["fk_outputs"])
+    assert np.abs(ee[:, 4:7] - ref[:, 4:7]).max() < 1e-12
+    sign = np.sign(np.sum(ee[:, :4] * ref[:, :4], axis=1))[:, None]
+    assert np.abs(ee[:, :4] * sign - ref[:, :4]).max() < 1e-12
+
+
+def test_jacobian_objective_gradient_against_pinned_oracle(golden):
+    r, _ = robot_and_chain("ur3e")
+    q = np.array(golden["fk_inputs"])
+    wl, wa = golden["oracle_weights"]
+    out = r.eval_batch(q, np.array(golden["oracle_target"]), wl, wa)
+    assert np.abs(out["jac"] - np.array(golden["oracle_jacobian"])).max() < 1e-12
+    f_ref, g_ref = np.array(golden["oracle_objective"]), np.array(golden["oracle_gradient"])
+    assert np.abs(out["f"] - f_ref).max() <= 1e-12 * np.abs(f_ref).max()
+    assert np.abs(out["grad"] - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
+
+
+@pytest.mark.parametrize("name", ["panda", "ur5", "snake20"])
+def test_evaluator_vs_oracle_random(name):
+    r, ch = robot_and_chain(name)
+    rng = np.random.default_rng(2)
+    B = 257  # ragged: not a multiple of the block size
+    q = rng.uniform(ch.lb, ch.ub, size=(B, ch.n))
+    tg = targets_for(ch, rng, B)
+    out = r.eval_batch(q, tg)
+    for i in range(0, B, 8):
+        _, ee = ch.fk(q[i])
+        assert np.abs(out["ee"][i, :7] - ee[:7]).max() < 1e-12
+        assert np.abs(out["jac"][i].reshape(ch.n, 6).T - ch.joint_jacobian(q[i])).max() < 1e-12
+        f, g = ch.objective(q[i], tg[i]), ch.objective_grad(q[i], tg[i])
+        assert abs(out["f"][i] - f) <= 1e-12 * max(1.0, f)
+        assert np.abs(out["grad"][i] - g).max() <= 1e-11 * max(1.0, np.abs(g).max())
+
+
+def test_evaluator_ee_offset_and_single_calls():
+    r, ch = robot_and_chain("ur3e")
+    q = np.array([0.3, -1.0, 0.8, 0.1, 1.2, -0.4])
+    off = O.pose8([0.1, 0.2, -0.1, 0.9695], [0.05, -0.02, 0.1])
+    off[:4] /= np.linalg.norm(off[:4])
+    M = np.array(r.fk(q, ee_offset=O.pose8_to_matrix(off)))
+    _, ee = ch.fk(q, off)
+    assert np.abs(M - O.pose8_to_matrix(ee)).max() < 1e-12
+    J = np.array(r.joint_jacobian(q, ee_offset=O.pose8_to_matrix(off)))
+    assert np.abs(J - ch.joint_jacobian(q, off)).max() < 1e-12
+    # C ABI single calls: column-major 4x4 / 6xn, caller frees (crates/optik-cpp/src/lib.rs:90-116)
+    import ctypes as C
+    lib = ob.load_library()
+    x = (C.c_double * 6)(*q)
+    m = ob._take(lib.optik_robot_fk(r._h, x), 16).reshape(4, 4).T
+    assert np.abs(m - O.pose8_to_matrix(ch.fk(q)[1])).max() < 1e-12
+    jac = ob._take(lib.optik_robot_joint_jacobian(r._h, x), 36).reshape(6, 6).T
+    assert np.abs(jac - ch.joint_jacobian(q)).max() < 1e-12
+
+
+# ------------------------------------------------------------------ solver vs twin, per restart seed
+@pytest.mark.parametrize("name,tile,R", [("panda", 8, 2048), ("panda", 32, 512), ("ur5", 8, 1024), ("ur5", 16, 256),
+                                          ("ur3e", 8, 512), ("snake20", 32, 512)])
+def test_attempts_match_twin_per_seed(name, tile, R):
+    r, ch = robot_and_chain(name)
+    rng = np.random.default_rng(42)
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    x0 = 0.5 * (ch.lb + ch.ub)
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R, tile=tile)
+    tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 0, R)
+    assert np.array_equal(st, tst), "success set / status differs from the CPU twin"
+    assert np.array_equal(ev, tev)
+    ok = st == 1
+    assert ok.sum() > R // 10
+    assert np.abs(q[ok] - tq[ok]).max() <= RAD_TOL
+    # stronger, informational-but-asserted: the arithmetic spec makes the two bit-identical
+    assert np.array_equal(q, tq) and np.array_equal(f, tf)
+    # every converged seed passes the reference's success predicate under the golden-pinned oracle
+    for i in np.where(ok)[0][:64]:
+        assert ch.objective(q[i], tgt) < cfg.tol_f
+        assert np.all(q[i] >= ch.lb) and np.all(q[i] <= ch.ub)
+
+
+def test_attempts_with_weights_tolerances_and_offsets():
+    r, ch = robot_and_chain("ur3e")
+    rng = np.random.default_rng(9)
+    x0 = np.zeros(6)
+    off = O.pose8([0, 0, 0.3826834, 0.9238795], [0.0, 0.05, 0.1])
+    off[:4] /= np.linalg.norm(off[:4])
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub), off)[1]
+    for kw in (dict(tol_f=1e-12), dict(tol_df=1e-4), dict(tol_dx=1e-3), dict(linear_weight=[1.0, 2.0, 0.5], angular_weight=[0.1, 1.0, 1.0])):
+        cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=128, **kw)
+        P = O.twin_params(tol_f=cfg.tol_f, tol_df=cfg.tol_df, tol_dx=cfg.tol_dx, wl=cfg.linear_weight, wa=cfg.angular_weight)
+        q, f, st, ev = r.ik_attempts(cfg, tgt, x0, 128, restart_begin=5, ee_offset=off)
+        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 5, 133, P, ee_offset=off)
+        assert np.array_equal(st, tst) and np.array_equal(ev, tev), kw
+        assert np.abs(q - tq).max() <= RAD_TOL, kw
+        assert cfg.is_success(st).sum() > 5, kw
+
+
+# ------------------------------------------------------------------ batched ik(): selection semantics
+@pytest.mark.parametrize("mode", ["speed", "quality"])
+@pytest.mark.parametrize("chunks", [1, 4, 0])
+def test_ik_batch_matches_reference_selection(mode, chunks):
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(7)
+    T, R = 96, 12
+    tg = targets_for(ch, rng, T)
+    x0 = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
+    cfg = ob.SolverConfig(solution_mode=mode, max_time=0.0, max_restarts=R)
+    q, f, st, extra = r.ik_batch(cfg, tg, x0, restarts=R, chunks=chunks, stats=True)
+    for t in range(T):
+        ref = O.twin_ik(ch, tg[t], x0[t], 0, R, mode)
+        assert bool(cfg.is_success(st[t])) == ref["found"], t
+        if ref["found"]:
+            assert int(extra["restart"][t]) == ref["restart"], t
+            assert np.abs(q[t] - ref["q"]).max() <= RAD_TOL
+            assert ch.objective(q[t], tg[t]) < cfg.tol_f
+    assert cfg.is_success(st).mean() > 0.9
+
+
+def test_ik_batch_device_path_matches_host_path():
+    import torch
+    r, ch = robot_and_chain("ur5")
+    rng = np.random.default_rng(3)
+    T = 1000
+    tg = targets_for(ch, rng, T)
+    x0 = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=8)
+    q, f, st = r.ik_batch(cfg, tg, x0, restarts=8)
+    dq, df, dst = r.ik_batch(cfg, torch.from_numpy(tg).cuda(), torch.from_numpy(x0).cuda(), restarts=8)
+    torch.cuda.synchronize()
+    assert np.array_equal(dq.cpu().numpy(), q) and np.array_equal(dst.cpu().numpy(), st)
+
+
+def test_restart_sharding_is_consistent():
+    """Splitting the restart range (multi-GPU restart sharding, waves) and re-selecting gives the same answer."""
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(5)
+    T = 32
+    tg = targets_for(ch, rng, T)
+    x0 = np.tile(0.5 * (ch.lb + ch.ub), (T, 1))
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=16)
+    q, f, st = r.ik_batch(cfg, tg, x0, restarts=16)
+    qa, fa, sa = r.ik_batch(cfg, tg, x0, restarts=8, restart_begin=0)
+    qb, fb, sb = r.ik_batch(cfg, tg, x0, restarts=8, restart_begin=8)
+    for t in range(T):
+        cands = [(np.sum((qq[t] - x0[t]) ** 2), qq[t]) for qq, ss in ((qa, sa), (qb, sb)) if cfg.is_success(ss[t])]
+        assert bool(cands) == bool(cfg.is_success(st[t]))
+        if cands:
+            assert np.array_equal(min(cands, key=lambda c: c[0])[1], q[t])
+
+
+# ------------------------------------------------------------------ the reference's own ik() tests (tests/test_ik.rs)
+def test_solution_forward_backward():  # tests/test_ik.rs:91-130
+    r, ch = robot_and_chain("ur3e")
+    rng = np.random.default_rng(42)
+    cfg = ob.SolverConfig(solution_mode="speed", tol_f=1e-12, max_time=0.0, max_restarts=25)
+    for _ in range(10):
+        x_target = rng.random(6)
+        T = np.array(r.fk(x_target))
+        sol = r.ik(cfg, T, [0.0] * 6)
+        assert sol is not None
+        assert np.abs(np.array(r.fk(sol[0])) - T).max() < 1e-6
+
+
+def test_determinism():  # tests/test_ik.rs:45-89
+    r, _ = robot_and_chain("ur3e")
+    r.set_parallelism(1)
+    T = np.array(r.fk(np.random.default_rng(42).random(6)))
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=25)
+    first = r.ik(cfg, T, [0.0] * 6)
+    assert first is not None
+    for _ in range(10):
+        again = r.ik(cfg, T, [0.0] * 6)
+        assert np.abs(np.array(again[0]) - np.array(first[0])).max() < 1e-6
+
+
+def test_solution_quality():  # tests/test_ik.rs:132-182
+    r, _ = robot_and_chain("ur3e")
+    rng = np.random.default_rng(42)
+    speed = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=15)
+    quality = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=15)
+    for _ in range(20):
+        T = np.array(r.fk(rng.random(6)))
+        x0 = [0.0] * 6
+        s, q = r.ik(speed, T, x0), r.ik(quality, T, x0)
+        assert s is not None and q is not None
+        assert np.linalg.norm(np.array(q[0]) - x0) <= np.linalg.norm(np.array(s[0]) - x0)
+
+
+def test_stopping_maxtime():  # tests/test_ik.rs:24-43: impossible goal returns None after ~max_time
+    import time
+    r, _ = robot_and_chain("ur3e")
+    T = np.eye(4)
+    T[:3, 3] = 100.0
+    r.ik(ob.SolverConfig(max_time=0.05), T, [0.0] * 6)  # warm-up (context, module load)
+    t0 = time.perf_counter()
+    out = r.ik(ob.SolverConfig(max_time=0.05), T, [0.0] * 6)
+    dt = time.perf_counter() - t0
+    assert out is None
+    assert abs(dt - 0.05) < 0.1
+
+
+def test_c_abi_ik_returns_malloced_solution():  # crates/optik-cpp/src/lib.rs:127-162, lib.cpp:105-120
+    import ctypes as C
+    r, ch = robot_and_chain("ur3e")
+    lib = ob.load_library()
+    qstar = np.array([0.5, -0.7, 0.9, 0.2, -0.4, 0.3])
+    M = O.pose8_to_matrix(ch.fk(qstar)[1])
+    tgt = (C.c_double * 16)(*M.T.ravel())  # column-major
+    x0 = (C.c_double * 6)(*([0.0] * 6))
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=25)._c()
+    p = lib.optik_robot_ik(r._h, C.byref(cfg), tgt, x0)
+    assert p
+    q = ob._take(p, 6)
+    assert ch.objective(q, ch.fk(qstar)[1]) < 1e-6
+    far = np.eye(4)
+    far[:3, 3] = 100.0
+    tgt2 = (C.c_double * 16)(*far.T.ravel())
+    assert not lib.optik_robot_ik(r._h, C.byref(cfg), tgt2, x0)  # NULL == no solution
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs)
+def test_config2_full_size_properties():
+    """Panda, 65 536 restart seeds to one target: every converged record re-evaluates below tol_f inside the limits
+    (checked on the GPU evaluator, spot-checked by the oracle), and a sample of seeds matches the twin exactly."""
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(42)
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    x0 = 0.5 * (ch.lb + ch.ub)
+    R = 65536
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R)
+    ok = st == 1
+    assert 0.2 < ok.mean() < 0.95
+    fe = r.eval_batch(q, tgt, want=("f",))["f"]
+    assert np.all(fe[ok] < cfg.tol_f)
+    assert np.allclose(fe, f, rtol=1e-9, atol=1e-18)  # evaluator kernel (backward recursion) vs solve kernel (scan)
+    assert np.all(q[ok] >= ch.lb) and np.all(q[ok] <= ch.ub)
+    idx = rng.choice(R, 256, replace=False)
+    for i in idx:
+        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1)
+        assert tst[0] == st[i] and tev[0] == ev[i] and np.array_equal(tq[0], q[i])
+    # Quality selection over all seeds == arg-min distance among converged
+    qb, fb, sb = r.ik_batch(cfg, tgt[None, :], x0[None, :], restarts=R)
+    d = np.sum((q[ok] - x0) ** 2, axis=1)
+    assert np.array_equal(qb[0], q[ok][np.argmin(d)])
