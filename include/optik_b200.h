@@ -140,7 +140,15 @@ typedef struct optik_gpu_batch_opts {
   uint64_t* restart_out;   /* [T] winning restart index, optional */
   int32_t* evals_out;      /* [T] objective evaluations spent on the target, optional */
   uint64_t* counters;      /* [3] += {attempts run, evaluations, converged attempts}, optional */
+  /* optik_gpu_ik_attempts only: also run the selection pass (lib.rs:397-413) over the records and write ONE
+   * candidate record of OPTIK_RECORD_HEAD + n doubles:
+   *   [0] found (1.0 / 0.0)  [1] score (Quality: ||q-x0||^2, Speed: restart index)  [2] restart index
+   *   [3] cost f(q)  [4] status  [5..7] 0  [8..8+n) q
+   * This is the record ranks exchange for a cross-GPU best-pick (optik_gpu_select_records). */
+  double* best_record_out;
 } optik_gpu_batch_opts;
+
+#define OPTIK_RECORD_HEAD 8
 
 /* Robot::ik() over T independent (target, x0) pairs in one launch.
  *   targets [T][8] pose8, x0 [T][n]  ->  q_out [T][n], cost_out [T] (objective value), status_out [T]
@@ -172,6 +180,12 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
  * semantics as optik_robot_ik.  Returns 1 = solution written to q_out[n], *cost_out; 0 = no solution; <0 = -(error). */
 int optik_robot_ik_ex(const optik_robot* robot, const optik_solver_config* config, const double* target_pose8,
                       const double* x0, const double* ee_offset_pose8, double* q_out, double* cost_out);
+
+/* Cross-GPU best-pick: the reference's selection rule (lib.rs:397-413) over `count` candidate records of
+ * OPTIK_RECORD_HEAD + n doubles (e.g. the output of an all-gather): converged first, then lowest score, then lowest
+ * restart index.  Device pointers, asynchronous on `stream`. */
+int optik_gpu_select_records(const optik_robot* robot, const double* records, uint32_t count, double* best_record_out,
+                             void* stream);
 
 /* Pinned host allocations for fast, truly asynchronous host<->device copies. */
 void* optik_host_alloc(uint64_t bytes);

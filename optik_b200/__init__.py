@@ -39,7 +39,10 @@ class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
     _fields_ = [("struct_size", C.c_uint32), ("restarts", C.c_uint32), ("restart_begin", C.c_uint64),
                 ("chunks", C.c_uint32), ("tile", C.c_uint32), ("max_evals", C.c_uint32), ("blocks", C.c_uint32),
                 ("memory", C.c_int32), ("ee_offset", C.c_void_p), ("restart_out", C.c_void_p),
-                ("evals_out", C.c_void_p), ("counters", C.c_void_p)]
+                ("evals_out", C.c_void_p), ("counters", C.c_void_p), ("best_record_out", C.c_void_p)]
+
+
+RECORD_HEAD = 8  # candidate record: [found, score, restart, cost, status, 0, 0, 0, q...]
 
 
 def data_path(name):
@@ -85,6 +88,7 @@ def load_library():
         "optik_gpu_ik_batch": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, C.c_uint64, vp, vp, vp, vp]),
         "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
         "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
+        "optik_gpu_select_records": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
         "optik_host_alloc": (vp, [C.c_uint64]),
         "optik_host_free": (None, [vp]),
     }
@@ -363,20 +367,61 @@ class Robot:
                                       q.ctypes.data, f.ctypes.data, st.ctypes.data, None))
         return (q, f, st, extra) if stats else (q, f, st)
 
-    def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None):
+    def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None,
+                    best=False, out=None, counters=None, record=None):
         """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
-        completion (no Speed-mode early exit) -- BASELINE config 2's output."""
+        completion (no Speed-mode early exit) -- BASELINE config 2's output.  best=True also runs the selection
+        pass (lib.rs:397-413) and appends the packed candidate record (RECORD_HEAD + n doubles:
+        [found, score, restart, cost, status, 0,0,0, q...]).  numpy = host path (out = preallocated, e.g. pinned,
+        buffers), torch CUDA tensors = device path on the current stream (no host sync)."""
         lib = load_library()
         c = config._c()
         n, R = self._n, int(restarts)
+        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset)
+        if _is_torch(target):
+            import torch
+            dev = target.device
+            assert target.is_cuda and x0.is_cuda and target.dtype == torch.float64 and x0.dtype == torch.float64
+            assert target.numel() == 8 and x0.numel() == n and target.is_contiguous() and x0.is_contiguous()
+            o.memory = 1
+            if out is None:
+                out = (torch.empty((R, n), dtype=torch.float64, device=dev), torch.empty((R,), dtype=torch.float64, device=dev),
+                       torch.empty((R,), dtype=torch.int32, device=dev), torch.empty((R,), dtype=torch.int32, device=dev))
+            q, f, st, ev = out
+            if best:
+                if record is None:
+                    record = torch.empty((RECORD_HEAD + n,), dtype=torch.float64, device=dev)
+                o.best_record_out = record.data_ptr()
+            if counters is not None:
+                o.counters = counters.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.data_ptr(), x0.data_ptr(), q.data_ptr(),
+                                             f.data_ptr(), st.data_ptr(), ev.data_ptr(), stream))
+            return (q, f, st, ev, record) if best else (q, f, st, ev)
         target = np.ascontiguousarray(target, dtype=np.float64).reshape(8)
         x0 = self._x(x0)
-        q, f = np.empty((R, n)), np.empty(R)
-        st, ev = np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32)
-        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset)
+        if out is None:
+            out = (np.empty((R, n)), np.empty(R), np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32))
+        q, f, st, ev = out
+        if best:
+            if record is None:
+                record = np.zeros(RECORD_HEAD + n)
+            o.best_record_out = record.ctypes.data
+        if counters is not None:
+            o.counters = counters.ctypes.data
         _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.ctypes.data, x0.ctypes.data,
                                          q.ctypes.data, f.ctypes.data, st.ctypes.data, ev.ctypes.data, None))
-        return q, f, st, ev
+        return (q, f, st, ev, record) if best else (q, f, st, ev)
+
+    def select_records(self, records, out=None):
+        """Best-pick (lib.rs:397-413) over gathered candidate records (W, RECORD_HEAD+n) CUDA tensor -> one record."""
+        import torch
+        assert records.is_cuda and records.dtype == torch.float64 and records.is_contiguous()
+        if out is None:
+            out = torch.empty((records.shape[1],), dtype=torch.float64, device=records.device)
+        stream = torch.cuda.current_stream(records.device).cuda_stream
+        _check(load_library().optik_gpu_select_records(self._h, records.data_ptr(), records.shape[0], out.data_ptr(), stream))
+        return out
 
     def eval_batch(self, q, targets=None, linear_weight=None, angular_weight=None, ee_offset=None,
                    want=("ee", "jac", "f", "grad")):

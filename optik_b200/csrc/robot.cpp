@@ -28,6 +28,7 @@ extern "C" int optik_launch_select(const SelectParams* p, void* stream);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n);
+extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
 
 namespace {
 
@@ -192,6 +193,13 @@ struct optik_robot {
     const int tiles[3] = {8, 16, 32};
     for (int i = 0; i < 3; i++) CUDA_TRY(optik_solve_occupancy(tiles[i], &occ[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // keep stream-ordered scratch cached across synchronisations (the default threshold of 0 returns it to the
+    // driver at every sync, which turns each host-path call into a fresh cudaMalloc)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     gpu_ready = true;
     return 0;
   }
@@ -271,7 +279,7 @@ bool config_valid(const optik_solver_config* c) {
 int solve_device(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
                  const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
                  double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
-                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s) {
+                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
   const int tile = choose_tile(r->n, o ? o->tile : 0);
   if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 8, 16 or 32 and >= num_positions");
   SolveParams P{};
@@ -302,7 +310,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const size_t off_f = direct ? 0 : carve(njobs * sizeof(double));
   const size_t off_st = direct ? 0 : carve(njobs * sizeof(int));
   const size_t off_score = carve(njobs * sizeof(double));
-  const size_t off_rs = (direct && d_restart) ? 0 : carve(njobs * sizeof(unsigned long long));
+  const bool restart_direct = direct && d_restart && !per_attempt_records;  // per-attempt: restart_out is the winner's
+  const size_t off_rs = restart_direct ? 0 : carve(njobs * sizeof(unsigned long long));
   const size_t off_ev = (direct && d_evals) ? 0 : carve(njobs * sizeof(int));
   const bool use_found = (cfg->solution_mode == OPTIK_MODE_SPEED) && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
@@ -312,7 +321,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   P.cand_f = direct ? d_f : (double*)(scratch + off_f);
   P.cand_status = direct ? d_status : (int*)(scratch + off_st);
   P.cand_score = (double*)(scratch + off_score);
-  P.cand_restart = (direct && d_restart) ? (unsigned long long*)d_restart : (unsigned long long*)(scratch + off_rs);
+  P.cand_restart = restart_direct ? (unsigned long long*)d_restart : (unsigned long long*)(scratch + off_rs);
   P.cand_evals = (direct && d_evals) ? d_evals : (int*)(scratch + off_ev);
   P.found = nullptr;
   if (use_found) {
@@ -320,10 +329,19 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
   }
   CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
+  if (per_attempt_records && d_best_record) {  // selection pass over the per-attempt records -> one packed record
+    SelectParams S{};
+    S.T = 1; S.C = P.C; S.n = n; S.mode = cfg->solution_mode;
+    S.cand_q = P.cand_q; S.cand_f = P.cand_f; S.cand_score = P.cand_score; S.cand_restart = P.cand_restart;
+    S.cand_status = P.cand_status; S.cand_evals = P.cand_evals;
+    S.tol_f = cfg->tol_f; S.tol_df_user = cfg->tol_df; S.tol_dx = cfg->tol_dx;
+    S.record_out = d_best_record;
+    CUDA_TRY(optik_launch_select(&S, s));
+  }
   if (!direct) {
     if (T > 0x7fffffffull) return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
     SelectParams S{};
-    S.T = T; S.C = P.C; S.n = n;
+    S.T = T; S.C = P.C; S.n = n; S.mode = cfg->solution_mode;
     S.cand_q = P.cand_q; S.cand_f = P.cand_f; S.cand_score = P.cand_score; S.cand_restart = P.cand_restart;
     S.cand_status = P.cand_status; S.cand_evals = P.cand_evals;
     S.tol_f = cfg->tol_f; S.tol_df_user = cfg->tol_df; S.tol_dx = cfg->tol_dx;
@@ -447,6 +465,14 @@ double* optik_robot_random_configuration(const optik_robot* robot) {
   return out;
 }
 
+int optik_gpu_select_records(const optik_robot* robot, const double* records, uint32_t count, double* best_record_out,
+                             void* stream) {
+  if (!robot || !records || !best_record_out || count == 0) return fail(OPTIK_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(robot->device));
+  CUDA_TRY(optik_launch_select_records(records, count, robot->n, best_record_out, stream));
+  return OPTIK_OK;
+}
+
 void* optik_host_alloc(uint64_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_last_error = "cudaMallocHost failed"; return nullptr; }
@@ -558,16 +584,18 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
     // seeds outside the limits cannot be checked without a sync; they are clamped by the kernel (documented)
     return solve_device(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
                         opts ? opts->restart_out : nullptr, per_attempt ? evals_all : (opts ? opts->evals_out : nullptr),
-                        opts ? opts->counters : nullptr, max_ns, per_attempt, s);
+                        opts ? opts->counters : nullptr, max_ns, per_attempt, s, opts ? opts->best_record_out : nullptr);
   }
   if (int rc = check_seeds_host(robot, x0, T)) return rc;
   size_t bytes = 0;
   auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
   const bool want_rs = opts && opts->restart_out, want_cnt = opts && opts->counters;
+  const bool want_best = per_attempt && opts && opts->best_record_out;
+  const uint64_t NR = per_attempt ? 1 : T;  // restart_out entries
   int32_t* evals_host = per_attempt ? evals_all : (opts ? opts->evals_out : nullptr);
   const size_t o_t = carve(T * 64), o_x = carve(T * n * 8), o_q = carve(NO * n * 8), o_f = carve(NO * 8),
-               o_s = carve(NO * 4), o_r = want_rs ? carve(NO * 8) : 0, o_e = evals_host ? carve(NO * 4) : 0,
-               o_c = want_cnt ? carve(24) : 0;
+               o_s = carve(NO * 4), o_r = want_rs ? carve(NR * 8) : 0, o_e = evals_host ? carve(NO * 4) : 0,
+               o_c = want_cnt ? carve(24) : 0, o_br = want_best ? carve((OPTIK_RECORD_HEAD + n) * 8) : 0;
   char* d = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
   CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, T * 64, cudaMemcpyHostToDevice, s));
@@ -576,12 +604,14 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   int rc = solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
                         (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
                         evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
-                        per_attempt, s);
+                        per_attempt, s, want_best ? (double*)(d + o_br) : nullptr);
   if (rc) { cudaFreeAsync(d, s); return rc; }
   CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, NO * 4, cudaMemcpyDeviceToHost, s));
-  if (want_rs) CUDA_TRY(cudaMemcpyAsync(opts->restart_out, d + o_r, NO * 8, cudaMemcpyDeviceToHost, s));
+  if (want_rs) CUDA_TRY(cudaMemcpyAsync(opts->restart_out, d + o_r, NR * 8, cudaMemcpyDeviceToHost, s));
+  if (want_best)
+    CUDA_TRY(cudaMemcpyAsync(opts->best_record_out, d + o_br, (OPTIK_RECORD_HEAD + n) * 8, cudaMemcpyDeviceToHost, s));
   if (evals_host) CUDA_TRY(cudaMemcpyAsync(evals_host, d + o_e, NO * 4, cudaMemcpyDeviceToHost, s));
   uint64_t cnt[3] = {0, 0, 0};
   if (want_cnt) CUDA_TRY(cudaMemcpyAsync(cnt, d + o_c, 24, cudaMemcpyDeviceToHost, s));

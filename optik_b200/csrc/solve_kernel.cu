@@ -448,8 +448,22 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     __syncthreads();
   }
   const unsigned long long win = t * P.C + s_idx[0];
-  for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[t * P.n + j] = P.cand_q[win * P.n + j];
-  if (threadIdx.x == 0) {
+  if (P.q_out)
+    for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[t * P.n + j] = P.cand_q[win * P.n + j];
+  if (P.record_out) {
+    double* rec = P.record_out + t * (8 + P.n);
+    for (int j = threadIdx.x; j < P.n; j += blockDim.x) rec[8 + j] = P.cand_q[win * P.n + j];
+    if (threadIdx.x == 0) {
+      const unsigned long long rr = P.cand_restart[win];
+      rec[0] = s_has[0] > 0 ? 1.0 : 0.0;
+      rec[1] = (P.mode == 2) ? (double)rr : P.cand_score[win];
+      rec[2] = (double)rr;
+      rec[3] = P.cand_f[win];
+      rec[4] = (double)P.cand_status[win];
+      rec[5] = rec[6] = rec[7] = 0.0;
+    }
+  }
+  if (threadIdx.x == 0 && P.f_out) {
     P.f_out[t] = P.cand_f[win];
     if (P.restart_out) P.restart_out[t] = P.cand_restart[win];
     P.status_out[t] = P.cand_status[win];
@@ -459,7 +473,34 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
 
 }  // namespace optik
 
+namespace optik {
+// Best-pick over gathered candidate records (one warp): converged first, lowest score, lowest restart index.
+__global__ void select_records_kernel(const double* __restrict__ rec, unsigned count, int n, double* __restrict__ out) {
+  const int len = 8 + n;
+  const unsigned lane = threadIdx.x;
+  double has = -1.0, score = 0.0, restart = 0.0;
+  unsigned idx = 0;
+  for (unsigned c = lane; c < count; c += 32) {
+    const double h = rec[c * len + 0], s = rec[c * len + 1], r = rec[c * len + 2];
+    const bool better = (h > has) || (h == has && (s < score || (s == score && r < restart)));
+    if (better) { has = h; score = s; restart = r; idx = c; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double h2 = __shfl_xor_sync(0xffffffffu, has, o), s2 = __shfl_xor_sync(0xffffffffu, score, o),
+                 r2 = __shfl_xor_sync(0xffffffffu, restart, o);
+    const unsigned i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    const bool better = (h2 > has) || (h2 == has && (s2 < score || (s2 == score && (r2 < restart || (r2 == restart && i2 < idx)))));
+    if (better) { has = h2; score = s2; restart = r2; idx = i2; }
+  }
+  for (int j = lane; j < len; j += 32) out[j] = rec[idx * len + j];
+}
+}  // namespace optik
+
 // ------------------------------------------------------------------ host launchers (called from robot.cpp)
+extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream) {
+  optik::select_records_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rec, count, n, out);
+  return (int)cudaGetLastError();
+}
 extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int threads = 128;

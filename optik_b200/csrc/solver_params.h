@@ -85,6 +85,8 @@ struct SelectParams {
   unsigned long long* restart_out;   // [T]
   int* status_out;                   // [T]
   int* evals_out;                    // [T] total evaluations spent on the target
+  double* record_out;                // [T][8+n] packed candidate record (see optik_b200.h), may be null
+  int mode;                          // 1 Quality, 2 Speed (record score)
 };
 
 struct EvalParams {

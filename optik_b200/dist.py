@@ -1,0 +1,97 @@
+"""Multi-GPU layer: one process per GPU, sharding with no data-path collective except the best-pick exchange.
+
+The reference has no distributed backend (single-process rayon); what shards here is its restart
+index space (crates/optik/src/lib.rs:298-301) and, for batches, the independent targets.
+
+  * restart sharding (BASELINE config 2, single-target calls): rank g runs restarts [g*R, (g+1)*R); every rank
+    keeps its best candidate; ONE all-gather of a (4+n)-double record per rank; every rank then applies the
+    reference's selection rule (lib.rs:397-413) to the gathered records -- Quality: arg-min ||q-x0||^2,
+    Speed: lowest converged restart index.
+  * target sharding (configs 3, 5): contiguous target ranges; selection is rank-local; one all-gather assembles
+    the result (optional).
+
+torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_range(total, rank, world):
+    """Contiguous [begin, end) of `total` items for `rank` of `world` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+RECORD_HEAD = 8  # [found, score, restart, cost, status, 0, 0, 0, q...]  (include/optik_b200.h)
+
+
+def pack_candidate(found, score, restart, cost, q, status=1.0):
+    """-> float64 candidate record (torch tensor on q's device) in the layout the select kernels use."""
+    import torch
+    f64 = lambda v: torch.as_tensor(v, dtype=torch.float64, device=q.device).reshape(())
+    head = torch.stack([f64(found), f64(score), f64(restart), f64(cost), f64(status), f64(0.0), f64(0.0), f64(0.0)])
+    return torch.cat([head, q.to(torch.float64).reshape(-1)])
+
+
+def select_candidates(records, as_tensor=False):
+    """Reference selection (lib.rs:397-413) over gathered records (W, RECORD_HEAD+n) with torch ops (CPU tests, and
+    the specification of optik_gpu_select_records): converged first, then lowest score, then lowest restart index.
+    Returns (index, record); with as_tensor=True only the record, without a host sync."""
+    import torch
+    found, score, restart = records[:, 0], records[:, 1], records[:, 2]
+    big = torch.finfo(torch.float64).max
+    key_score = torch.where(found > 0, score, torch.full_like(score, big))
+    best = key_score.min()
+    tie = (key_score == best) & ((found > 0) | (found.max() <= 0))
+    r = torch.where(tie, restart, torch.full_like(restart, big))
+    if as_tensor:
+        return records.index_select(0, torch.argmin(r).reshape(1))[0]
+    idx = int(torch.argmin(r))
+    return idx, records[idx]
+
+
+def all_gather_records(record, group=None, out=None):
+    """One all-gather of a small fixed-size record per rank -> (world, len) tensor.  NCCL for CUDA tensors."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return record.unsqueeze(0)
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world,) + tuple(record.shape), dtype=record.dtype, device=record.device)
+    if record.is_cuda:
+        dist.all_gather_into_tensor(out, record.contiguous(), group=group)  # NCCL over NVLink / NVSwitch
+    else:
+        dist.all_gather(list(out.unbind(0)), record.contiguous(), group=group)  # gloo (CPU tests)
+    return out
+
+
+def ik_restart_sharded(robot, config, target, x0, restarts_per_rank, rank=0, world=1, group=None, tile=0,
+                       counters=None, out=None, record=None, gathered=None, best=None):
+    """One target, restarts sharded over ranks: rank g runs [g*R, (g+1)*R), selects its best candidate on the
+    device (select_kernel), ONE all-gather of the candidate record, then the same selection rule over the gathered
+    records (optik_gpu_select_records) gives every rank the GLOBAL best under config.solution_mode.
+    Returns (best_record, local_records); everything stays on the device, no host sync.
+    target (8,), x0 (n,) CUDA float64 tensors; record/gathered/best are optional preallocated buffers."""
+    R = int(restarts_per_rank)
+    q, f, st, ev, rec = robot.ik_attempts(config, target, x0, R, restart_begin=rank * R, tile=tile, best=True,
+                                          counters=counters, out=out, record=record)
+    if world == 1:
+        return rec, (q, f, st, ev)
+    allrec = all_gather_records(rec, group, out=gathered)
+    return robot.select_records(allrec, out=best), (q, f, st, ev)
+
+
+def ik_batch_target_sharded(robot, config, targets, x0, restarts, rank=0, world=1, group=None, gather=True, **kw):
+    """T targets sharded contiguously over ranks (selection is local).  targets/x0 are this rank's CUDA tensors for
+    its shard; with gather=True the per-target results are assembled on every rank with one all-gather."""
+    import torch
+    import torch.distributed as dist
+    q, f, st = robot.ik_batch(config, targets, x0, restarts=restarts, **kw)
+    if not gather or world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return q, f, st
+    n = q.shape[1]
+    rec = torch.cat([q, f[:, None], st.to(torch.float64)[:, None]], dim=1).contiguous()
+    out = torch.empty((world * rec.shape[0], n + 2), dtype=torch.float64, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)  # equal shard sizes required
+    return out[:, :n], out[:, n], out[:, n + 1].to(torch.int32)

@@ -23,7 +23,7 @@ def build(force: bool = False) -> str:
     # -ffp-contract=off: every fused multiply-add in the solver twin is an
     # explicit fma() so that it is bit-identical to the CUDA kernel (which is
     # compiled with -fmad=false).  -mfma only makes fma() a single instruction.
-    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+    cmd = ["gcc", "-O3", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
            "-pthread", "-o", OUT] + srcs + ["-lm"]
     import platform
     if platform.machine() in ("x86_64", "AMD64"):

@@ -221,3 +221,21 @@ def twin_ik(chain, target, x0, r_begin, r_end, mode="speed", params=None, ee_off
                             2 if mode == "speed" else 1, _p(q), C.byref(f), C.byref(st), C.byref(rs))
     assert found >= 0, found
     return dict(found=bool(found), q=q, f=f.value, status=st.value, restart=rs.value)
+
+
+def ref_ik_threaded(chain, target, x0, r_begin, r_end, mode="quality", threads=1, params=None, ee_offset=None):
+    """The reference's parallel restart driver (lib.rs:297-413) over the twin solver, `threads` pthread workers.
+    Returns dict(found, q, f, restart, attempts, evals, converged)."""
+    params = params or twin_params()
+    q = np.zeros(chain.n)
+    f = C.c_double()
+    rs = C.c_uint64()
+    stats = (C.c_uint64 * 3)()
+    fn = lib().ref_ik_threaded
+    fn.argtypes = [dp, C.c_int, dp, C.POINTER(TwinParams), dp, dp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, dp,
+                   C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    found = fn(_p(chain.arr), chain.njoints, _p(None if ee_offset is None else _d(ee_offset)), C.byref(params),
+               _p(_d(target)), _p(_d(x0)), int(r_begin), int(r_end), 2 if mode == "speed" else 1, int(threads), _p(q),
+               C.byref(f), C.byref(rs), stats)
+    assert found >= 0
+    return dict(found=bool(found), q=q, f=f.value, restart=rs.value, attempts=stats[0], evals=stats[1], converged=stats[2])

@@ -36,7 +36,7 @@ enum { /* attempt status; mirrored by optik_b200/csrc/solve_kernel.cu */
   ST_SKIPPED = 7    /* not run: timeout / Speed-mode early exit         */
 };
 
-typedef struct {
+typedef struct twin_params {
   double tol_f, tol_df_eff, tol_df_user, tol_dx;
   double wl[3], wa[3];
   int weighted, max_evals;
@@ -45,7 +45,7 @@ typedef struct {
   int stall_count;  /* this many consecutive slow steps => ST_STUCK */
 } twin_params;
 
-typedef struct {
+typedef struct twin_chain {
   int n;
   int type[MAX_DOF];
   v3 ot[MAX_DOF], ax[MAX_DOF];
@@ -60,6 +60,11 @@ typedef struct {
   double Jr[MAX_DOF][6];
   se3t ee;
 } twin_eval;
+
+size_t twin_chain_sizeof(void) { return sizeof(twin_chain); }
+int twin_chain_n(const twin_chain* c) { return c->n; }
+const double* twin_chain_slb(const twin_chain* c) { return c->slb; }
+const double* twin_chain_sub(const twin_chain* c) { return c->sub; }
 
 static se3t se3_from_pose8(const double* p) {
   se3t r;

@@ -275,3 +275,41 @@ def test_config2_full_size_properties():
     qb, fb, sb = r.ik_batch(cfg, tgt[None, :], x0[None, :], restarts=R)
     d = np.sum((q[ok] - x0) ** 2, axis=1)
     assert np.array_equal(qb[0], q[ok][np.argmin(d)])
+
+
+# ------------------------------------------------------------------ best-pick records (cross-GPU exchange building blocks)
+@pytest.mark.parametrize("mode", ["speed", "quality"])
+def test_attempts_best_record_matches_reference_selection(mode):
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(21)
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    x0 = rng.uniform(ch.lb, ch.ub)
+    cfg = ob.SolverConfig(solution_mode=mode, max_time=0.0, max_restarts=300)
+    q, f, st, ev, rec = r.ik_attempts(cfg, tgt, x0, 300, restart_begin=40, best=True)
+    ref = O.twin_ik(ch, tgt, x0, 40, 340, mode)
+    assert ref["found"] and rec[0] == 1.0
+    assert int(rec[2]) == ref["restart"] and rec[4] == ref["status"] and rec[3] == ref["f"]
+    assert np.array_equal(rec[8:], ref["q"])
+    if mode == "quality":
+        assert np.isclose(rec[1], np.sum((ref["q"] - x0) ** 2), rtol=1e-12)
+    else:
+        assert rec[1] == ref["restart"]
+
+
+def test_select_records_kernel_matches_rule():
+    import torch
+    from optik_b200 import dist as obd
+    r, _ = robot_and_chain("panda")
+    rng = np.random.default_rng(8)
+    for count in (1, 2, 8, 33, 100):
+        rec = rng.random((count, obd.RECORD_HEAD + 7))
+        rec[:, 0] = rng.random(count) < 0.6
+        rec[:, 1] = np.round(rec[:, 1], 1)  # force score ties
+        rec[:, 2] = rng.permutation(count)
+        t = torch.from_numpy(rec).cuda()
+        got = r.select_records(t).cpu()
+        idx, want = obd.select_candidates(torch.from_numpy(rec))
+        if rec[:, 0].max() > 0:
+            assert torch.equal(got, want), count
+        else:
+            assert got[0] == 0.0
