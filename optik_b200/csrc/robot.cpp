@@ -262,6 +262,8 @@ void fill_common(const optik_robot* r, const optik_solver_config* cfg, const dou
     P.wa[i] = cfg->angular_weight[i];
     if (P.wl[i] != 1.0 || P.wa[i] != 1.0) P.weighted = 1;
   }
+  P.has_prismatic = 0;
+  for (const optik::Joint& J : r->joints) if (J.type == optik::PRISMATIC) P.has_prismatic = 1;
   P.max_evals = max_evals ? (int)max_evals : OPTIK_LM_MAX_EVALS;
   P.lambda0 = OPTIK_LM_LAMBDA0; P.lambda_dec = OPTIK_LM_LAMBDA_DEC; P.lambda_inc = OPTIK_LM_LAMBDA_INC;
   P.lambda_min = OPTIK_LM_LAMBDA_MIN; P.lambda_max = OPTIK_LM_LAMBDA_MAX;

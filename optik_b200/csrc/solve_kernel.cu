@@ -22,6 +22,10 @@
 #include "dmath.cuh"
 #include "solver_params.h"
 
+#ifndef OPTIK_SOLVE_MIN_BLOCKS
+#define OPTIK_SOLVE_MIN_BLOCKS 3
+#endif
+
 namespace optik {
 
 // ------------------------------------------------------------------ TMA staging
@@ -86,31 +90,37 @@ DEV se3 shfl_se3(se3 T, int src) {
 struct Joint {
   v3 ot, ax;
   qt oq;
-  double lb, ub, slb, sub;
-  int type;  // 0 revolute, 1 prismatic, 2 padding lane
+  double lb, ub;
+  int type;  // 0 revolute, 1 prismatic, 2 fixed transform (tip lane / padding lane)
 };
-DEV Joint load_joint(const double* s_chain, int lane, int n) {
+DEV se3 load_pose8(const double* p) {
+  se3 r;
+  r.q.x = p[0]; r.q.y = p[1]; r.q.z = p[2]; r.q.w = p[3];
+  r.t = mk3(p[4], p[5], p[6]);
+  return r;
+}
+// tip handling rule (depends on n only, so every tile width gives the same bits): the fixed tip transform rides
+// the scan in lane n unless n is exactly a tile width (8, 16, 32), where no spare lane exists.
+DEV bool tip_in_scan(int n) { return !(n == 8 || n == 16 || n == 32); }
+
+// lane < n: joint record; lane == n (when the tip rides the scan): origin = tip; lanes beyond: identity
+DEV Joint load_joint(const double* s_chain, const se3& tip, int lane, int n) {
   Joint J;
+  J.ot = mk3(0, 0, 0); J.ax = mk3(0, 0, 0);
+  J.oq.x = J.oq.y = J.oq.z = 0; J.oq.w = 1;
+  J.lb = J.ub = 0;
+  J.type = 2;
   if (lane < n) {
     const double* j = s_chain + OPTIK_CHAIN_STRIDE * lane;
     J.ot = mk3(j[0], j[1], j[2]);
     J.type = (int)j[3];
     J.oq.x = j[4]; J.oq.y = j[5]; J.oq.z = j[6]; J.oq.w = j[7];
     J.ax = mk3(j[8], j[9], j[10]);
-    J.lb = j[12]; J.ub = j[13]; J.slb = j[14]; J.sub = j[15];
-  } else {  // padding lane: identity transform, zero Jacobian column
-    J.ot = mk3(0, 0, 0); J.ax = mk3(0, 0, 0);
-    J.oq.x = J.oq.y = J.oq.z = 0; J.oq.w = 1;
-    J.lb = J.ub = J.slb = J.sub = 0;
-    J.type = 2;
+    J.lb = j[12]; J.ub = j[13];
+  } else if (lane == n && tip_in_scan(n)) {
+    J.oq = tip.q; J.ot = tip.t;
   }
   return J;
-}
-DEV se3 load_pose8(const double* p) {
-  se3 r;
-  r.q.x = p[0]; r.q.y = p[1]; r.q.z = p[2]; r.q.w = p[3];
-  r.t = mk3(p[4], p[5], p[6]);
-  return r;
 }
 DEV v3 weight3(qt tq, const double* w, v3 u) {  // R_tgt^T diag(w) R_tgt u   (objective.rs:13-35)
   v3 a = qrot(tq, u);
@@ -121,9 +131,13 @@ DEV v3 weight3(qt tq, const double* w, v3 u) {  // R_tgt^T diag(w) R_tgt u   (ob
 // ------------------------------------------------------------------ one objective evaluation (all lanes)
 // Restates kinematics.rs:123-196 (FK scan, body Jacobian), math.rs:40-203 (so3/se3 log, d-log), objective.rs:7-110
 // (residual, weights, task Jacobian).  Outputs: f and r[6] (tile-uniform), Jr[6] (this lane's task-Jacobian column).
+// FK runs IN THE TARGET'S FRAME: lane 0's origin was pre-multiplied by T_tgt^-1 when the job started, so the scan
+// yields the pose error X = T_tgt^-1 * T_ee (objective.rs:48-49) directly; the body-frame Jacobian does not depend on
+// the world frame.  `tgt_q` (the target rotation) is only read on the weighted path.
 template <int TILE>
-DEV void evaluate(const Joint& J, const se3& tip, const se3& tgt, const double* wl, const double* wa, int weighted,
-                  int n, int lane, double q, double& f, double* r, double* Jr, se3* ee_out = nullptr) {
+DEV void evaluate(const Joint& J, const se3& O, const double* s_tip, const double* tgt_q, const double* wl,
+                  const double* wa, int weighted, int has_prismatic, int n, int lane, double q, double& f, double* r,
+                  double* Jr) {
   // lane-local transform origin_j * motion_j(q_j)
   se3 T;
   {
@@ -131,27 +145,31 @@ DEV void evaluate(const Joint& J, const se3& tip, const se3& tgt, const double* 
     dsincos(0.5 * q, s, c);
     qt qa;
     qa.x = J.ax.x * s; qa.y = J.ax.y * s; qa.z = J.ax.z * s; qa.w = c;
-    const qt qrev = qmul(J.oq, qa);
-    const v3 tpri = add3(J.ot, qrot(J.oq, scale3(J.ax, q)));
-    T.q = (J.type == 0) ? qrev : J.oq;
-    T.t = (J.type == 1) ? tpri : J.ot;
+    const qt qrev = qmul(O.q, qa);
+    T.q = (J.type == 0) ? qrev : O.q;
+    T.t = O.t;
+    if (has_prismatic) {  // grid-uniform
+      const v3 tpri = add3(O.t, qrot(O.q, scale3(J.ax, q)));
+      if (J.type == 1) T.t = tpri;
+    }
   }
   // Kogge-Stone inclusive scan of SE(3) products over the tile
+  const bool fold = tip_in_scan(n);
+  const int m = fold ? n + 1 : n;
 #pragma unroll
   for (int d = 1; d < TILE; d <<= 1) {
-    if (d < n) {  // tile-uniform: n is a kernel constant
+    if (d < m) {  // grid-uniform: n is a kernel constant
       const se3 up = shfl_up_se3<TILE>(T, d);
       const se3 c = se3mul(up, T);
       if (lane >= d) T = c;
     }
   }
-  const se3 ee = se3mul(shfl_se3<TILE>(T, n - 1), tip);
-  if (ee_out) *ee_out = ee;
-  // pose error X = T_tgt^-1 * T_ee   (objective.rs:48-49)
-  const qt xq = qmul(qconj(tgt.q), ee.q);
-  const v3 xt = qrot_inv(tgt.q, sub3(ee.t, tgt.t));
-  double qw = xq.w;
-  v3 v = mk3(xq.x, xq.y, xq.z);
+  se3 ee = shfl_se3<TILE>(T, m - 1);
+  if (!fold) ee = se3mul(ee, load_pose8(s_tip));
+  // pose error X == ee (target frame)
+  double qw = ee.q.w;
+  v3 v = mk3(ee.q.x, ee.q.y, ee.q.z);
+  const v3 xt = ee.t;
   if (!(qw >= 0.0)) { qw = -qw; v = neg3(v); }  // double cover, math.rs:43-47
   const double vn2 = dot3(v, v);
   double k, th2, ce, bq;
@@ -177,7 +195,11 @@ DEV void evaluate(const Joint& J, const se3& tip, const se3& tgt, const double* 
   const v3 wxt = cross3(w, xt);
   const v3 elin = axpy3(ce, cross3(w, wxt), axpy3(-0.5, wxt, xt));  // V^-1 t
   v3 rl = elin, ra = w;
-  if (weighted) { rl = weight3(tgt.q, wl, elin); ra = weight3(tgt.q, wa, w); }
+  qt tq;
+  if (weighted) {
+    tq.x = tgt_q[0]; tq.y = tgt_q[1]; tq.z = tgt_q[2]; tq.w = tgt_q[3];
+    rl = weight3(tq, wl, elin); ra = weight3(tq, wa, w);
+  }
   r[0] = rl.x; r[1] = rl.y; r[2] = rl.z; r[3] = ra.x; r[4] = ra.y; r[5] = ra.z;
   f = dot6(r, r);
   // Q = C*J scalars (math.rs:160-169)
@@ -188,9 +210,9 @@ DEV void evaluate(const Joint& J, const se3& tip, const se3& tgt, const double* 
   // this lane's body-Jacobian column (kinematics.rs:171-193) -> task column Jlog6 * col (objective.rs:79-81)
   const v3 axw = qrot(T.q, J.ax);
   const v3 lw = cross3(axw, sub3(ee.t, T.t));
-  const v3 lin = qrot_inv(ee.q, (J.type == 0) ? lw : axw);
+  v3 lin = qrot_inv(ee.q, lw);
   v3 ang = qrot_inv(ee.q, axw);
-  if (J.type != 0) ang = mk3(0, 0, 0);
+  if (has_prismatic && J.type == 1) { lin = ang; ang = mk3(0, 0, 0); }
   const v3 wxa = cross3(w, ang);
   const v3 ja = axpy3(ce, cross3(w, wxa), axpy3(0.5, wxa, ang));
   const v3 wxl = cross3(w, lin);
@@ -198,46 +220,13 @@ DEV void evaluate(const Joint& J, const se3& tip, const se3& tgt, const double* 
   const double wu = dot3(w, ja), tu = dot3(xt, ja);
   const v3 cu = axpy3(da, ja, axpy3(ce * tu, w, axpy3(wu, cv, scale3(cross3(xt, ja), 0.5))));
   v3 top = add3(jl, cu), bot = ja;
-  if (weighted) { top = weight3(tgt.q, wl, top); bot = weight3(tgt.q, wa, bot); }
+  if (weighted) { top = weight3(tq, wl, top); bot = weight3(tq, wa, bot); }
   const bool live = (J.type != 2);
   Jr[0] = live ? top.x : 0.0; Jr[1] = live ? top.y : 0.0; Jr[2] = live ? top.z : 0.0;
   Jr[3] = live ? bot.x : 0.0; Jr[4] = live ? bot.y : 0.0; Jr[5] = live ? bot.z : 0.0;
 }
 
-// LDL^T solve of the SPD 6x6 system (lower triangle of A in packed row order a*(a+1)/2+b)
-DEV void ldl6_solve(const double* Ap, const double* r, double* y) {
-  double L[6][6], D[6], inv[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    double dj = Ap[j * (j + 1) / 2 + j];
-#pragma unroll
-    for (int k = 0; k < j; k++) dj = fma(-(L[j][k] * L[j][k]), D[k], dj);
-    D[j] = dj;
-    inv[j] = 1.0 / dj;
-#pragma unroll
-    for (int i = j + 1; i < 6; i++) {
-      double s = Ap[i * (i + 1) / 2 + j];
-#pragma unroll
-      for (int k = 0; k < j; k++) s = fma(-(L[i][k] * L[j][k]), D[k], s);
-      L[i][j] = s * inv[j];
-    }
-  }
-  double z[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    double s = r[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) s = fma(-L[i][k], z[k], s);
-    z[i] = s;
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; i--) {
-    double s = z[i] * inv[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; k++) s = fma(-L[k][i], y[k], s);
-    y[i] = s;
-  }
-}
+#include "ldl6.cuh"
 
 DEV unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -247,37 +236,39 @@ DEV unsigned long long globaltimer_ns() {
 
 // ------------------------------------------------------------------ the solve kernel
 template <int TILE>
-__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ SolveParams P) {
+__global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(const __grid_constant__ SolveParams P) {
   __shared__ alignas(128) double s_chain[OPTIK_MAX_DOF * OPTIK_CHAIN_STRIDE + 8];
+  __shared__ alignas(16) double s_tip[8];
   __shared__ alignas(8) uint64_t s_bar;
   stage_chain_tma(s_chain, &s_bar, P.chain, P.chain_bytes);
 
   const int n = P.n;
   const int lane = threadIdx.x % TILE;
-  const unsigned long long tiles_per_block = blockDim.x / TILE;
-  const unsigned long long total_tiles = tiles_per_block * gridDim.x;
+  const unsigned tiles_per_block = blockDim.x / TILE;
+  const unsigned long long total_tiles = (unsigned long long)tiles_per_block * gridDim.x;
   const unsigned long long njobs = P.T * (unsigned long long)P.C;
-  const Joint J = load_joint(s_chain, lane, n);
-  const se3 tip = se3mul(load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), load_pose8(P.ee_offset));
+  if (threadIdx.x == 0) {  // tip = fixed tip joint * ee_offset, once per block
+    const se3 tip = se3mul(load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), load_pose8(P.ee_offset));
+    s_tip[0] = tip.q.x; s_tip[1] = tip.q.y; s_tip[2] = tip.q.z; s_tip[3] = tip.q.w;
+    s_tip[4] = tip.t.x; s_tip[5] = tip.t.y; s_tip[6] = tip.t.z; s_tip[7] = 0.0;
+  }
+  __syncthreads();
+  const Joint J = load_joint(s_chain, load_pose8(s_tip), lane, n);
   const bool speed = (P.mode == 2);
   const unsigned long long t_start = P.max_ns ? globaltimer_ns() : 0ull;
 
   // ---- tile state (uniform across the tile unless marked "lane")
-  unsigned long long job = blockIdx.x * tiles_per_block + threadIdx.x / TILE;
+  unsigned long long job = (unsigned long long)blockIdx.x * tiles_per_block + threadIdx.x / TILE;
   unsigned long long tgt_id = 0, r_idx = 0;
-  bool need_job = true, running = false, done = false;
-  se3 tgt = tip;
-  double x0 = 0.0;                                   // lane
-  double qc = 0.0, qt_ = 0.0;                        // lane: current / trial joint value
+  bool need_job = true, running = false, done = false, best_has = false;
+  se3 O;                          // lane: this lane's origin (lane 0: pre-multiplied by T_tgt^-1 per job)
+  O.q = J.oq; O.t = J.ot;
+  double x0 = 0.0;                // lane
+  double qc = 0.0, qt_ = 0.0;     // lane: current / trial joint value
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, Jc[6] = {0, 0, 0, 0, 0, 0};  // current f, r, (lane) Jr column
-  double lambda = P.lambda0;
-  int have_cur = 0, slow = 0, evals = 0;
-  // per-job best candidate
-  bool best_has = false;
-  double best_q = 0.0, best_f = 0.0, best_score = 0.0;  // best_q: lane
-  unsigned long long best_r = 0;
-  int best_status = OPTIK_ST_SKIPPED, job_evals = 0;
-  unsigned long long n_attempts = 0, n_evals = 0, n_conv = 0;
+  double lambda = P.lambda0, best_score = 0.0;
+  int have_cur = 0, slow = 0, evals = 0, job_evals = 0;
+  unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
 
   for (;;) {
     // ---------------- transitions: pick the next attempt for tiles that are idle (no shuffles in here)
@@ -287,10 +278,22 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
           if (job >= njobs) { done = true; break; }
           tgt_id = job / P.C;
           r_idx = P.r_begin + job % P.C;
-          tgt = load_pose8(P.targets + 8 * tgt_id);
           x0 = (lane < n) ? P.x0[tgt_id * n + lane] : 0.0;
-          best_has = false; best_status = OPTIK_ST_SKIPPED; best_f = 0.0; best_score = 0.0; best_r = r_idx;
-          best_q = x0; job_evals = 0;
+          if (lane == 0) {  // FK in the target's frame: O_0 <- T_tgt^-1 * origin_0
+            const se3 tgt = load_pose8(P.targets + 8 * tgt_id);
+            se3 ti;
+            ti.q = qconj(tgt.q);
+            ti.t = neg3(qrot(ti.q, tgt.t));
+            se3 o0;
+            o0.q = J.oq; o0.t = J.ot;
+            O = se3mul(ti, o0);
+          }
+          best_has = false; best_score = 0.0; job_evals = 0;
+          if (lane < n) P.cand_q[job * n + lane] = x0;  // record of a chunk that runs no attempt
+          if (lane == 0) {
+            P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_idx;
+            P.cand_status[job] = OPTIK_ST_SKIPPED;
+          }
           need_job = false;
         }
         bool skip = r_idx >= P.r_end;
@@ -298,21 +301,16 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
         if (!skip && P.max_ns) skip = (globaltimer_ns() - t_start) > P.max_ns;
         if (!skip) {  // start restart r_idx: restart 0 = caller's seed, i>=1 = ChaCha8 stream i (lib.rs:360-370)
           double q0 = x0;
-          if (r_idx != 0) q0 = uniform_f64(chacha8_u64(P.key, (unsigned long long)(lane >> 3), r_idx, lane), J.slb, J.sub);
+          if (r_idx != 0 && lane < n) {
+            const double* j = s_chain + OPTIK_CHAIN_STRIDE * lane;
+            q0 = uniform_f64(chacha8_u64(P.key, (unsigned long long)(lane >> 3), r_idx, lane), j[14], j[15]);
+          }
           qt_ = fmin(fmax(q0, J.lb), J.ub);
           have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
           running = true;
           break;
         }
-        // job finished: write its candidate record
-        if (lane < n) P.cand_q[job * n + lane] = best_q;
-        if (lane == 0) {
-          P.cand_f[job] = best_f;
-          P.cand_score[job] = best_score;
-          P.cand_restart[job] = best_r;
-          P.cand_status[job] = best_status;
-          P.cand_evals[job] = job_evals;
-        }
+        if (lane == 0) P.cand_evals[job] = job_evals;  // job finished
         job += total_tiles;
         need_job = true;
       }
@@ -321,7 +319,7 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
 
     // ---------------- evaluate the trial point (every lane of the warp, uniform instruction stream)
     double ft, rt[6], Jt[6];
-    evaluate<TILE>(J, tip, tgt, P.wl, P.wa, P.weighted, n, lane, qt_, ft, rt, Jt);
+    evaluate<TILE>(J, O, s_tip, P.targets + 8 * tgt_id, P.wl, P.wa, P.weighted, P.has_prismatic, n, lane, qt_, ft, rt, Jt);
 
     // ---------------- bookkeeping (mirrors NLopt's stop tests as the reference configures them, lib.rs:345-347)
     int status = OPTIK_ST_NONE;
@@ -347,6 +345,10 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
       }
       if (status == OPTIK_ST_NONE && evals >= P.max_evals) status = OPTIK_ST_ITERCAP;
       if (status == OPTIK_ST_NONE && P.max_ns && (globaltimer_ns() - t_start) > P.max_ns) status = OPTIK_ST_SKIPPED;
+      // should_exit (lib.rs:308): a lower restart index of this target already converged
+      if (status == OPTIK_ST_NONE && speed && P.found &&
+          *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx)
+        status = OPTIK_ST_SKIPPED;
     }
     const bool success = (P.tol_f >= 0.0 && status == OPTIK_ST_STOPVAL) ||
                          (P.tol_df_user >= 0.0 && status == OPTIK_ST_FTOL) ||
@@ -359,17 +361,21 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
     }
     if (status != OPTIK_ST_NONE) {  // attempt over
       n_attempts++; n_evals += evals; job_evals += evals;
+      // r_idx only grows within a chunk, so on score ties the lower index is kept
+      const bool record = success ? (!best_has || score < best_score) : !best_has;
+      if (record) {  // the chunk's candidate record lives in HBM, not in registers
+        if (lane < n) P.cand_q[job * n + lane] = qt_;
+        if (lane == 0) {
+          P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
+        }
+      }
       if (success) {
         n_conv++;
-        if (!best_has || score < best_score) {  // r_idx only grows within a chunk: ties keep the lower index
-          best_has = true; best_q = qt_; best_f = ft; best_score = score; best_r = r_idx; best_status = status;
-        }
+        if (record) { best_has = true; best_score = score; }
         if (speed) {
           if (P.found && lane == 0) atomicMin(P.found + tgt_id, r_idx);
           r_idx = P.r_end;  // first success ends the chunk (lib.rs:381-387, 411)
         }
-      } else if (!best_has) {
-        best_q = qt_; best_f = ft; best_r = r_idx; best_status = status;
       }
       if (r_idx < P.r_end) r_idx += P.C;
       running = false;
@@ -384,23 +390,26 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ Solv
     const double g = dot6(rc, Jc);
     const bool pinned = (qc <= J.lb && g > 0.0) || (qc >= J.ub && g < 0.0);
     const double m = (pinned || lane >= n) ? 0.0 : 1.0;
+    double Jm[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) Jm[a] = m * Jc[a];
     double Ap[21];
 #pragma unroll
     for (int a = 0; a < 6; a++)
 #pragma unroll
-      for (int b = 0; b <= a; b++) Ap[a * (a + 1) / 2 + b] = tile_sum<TILE>(m * (Jc[a] * Jc[b]));
+      for (int b = 0; b <= a; b++) Ap[a * (a + 1) / 2 + b] = tile_sum<TILE>(Jm[a] * Jc[b]);
 #pragma unroll
     for (int a = 0; a < 6; a++) Ap[a * (a + 1) / 2 + a] = Ap[a * (a + 1) / 2 + a] + lambda;
     double y[6];
     ldl6_solve(Ap, rc, y);
-    const double dq = -(m * dot6(Jc, y));
+    const double dq = -dot6(Jm, y);
     qt_ = fmin(fmax(qc + dq, J.lb), J.ub);
   }
 
   if (P.counters && lane == 0) {
-    atomicAdd(P.counters + 0, n_attempts);
-    atomicAdd(P.counters + 1, n_evals);
-    atomicAdd(P.counters + 2, n_conv);
+    atomicAdd(P.counters + 0, (unsigned long long)n_attempts);
+    atomicAdd(P.counters + 1, (unsigned long long)n_evals);
+    atomicAdd(P.counters + 2, (unsigned long long)n_conv);
   }
 }
 

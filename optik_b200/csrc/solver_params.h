@@ -49,6 +49,7 @@ struct SolveParams {
   double tol_f, tol_df_eff, tol_df_user, tol_dx;
   double wl[3], wa[3];
   int weighted;
+  int has_prismatic;  // any prismatic joint in the chain (grid-uniform: lets the revolute-only path skip dead math)
   // LM constants
   int max_evals;
   double lambda0, lambda_dec, lambda_inc, lambda_min, lambda_max, stall_rel;

@@ -113,33 +113,47 @@ static inline v3 weight3(qt tq, const double w[3], v3 u) {
   return qt_rot_inv(tq, a);
 }
 
+/* tip handling rule (depends on n only, so every tile width gives the same bits): the fixed tip transform rides
+ * the scan as entry n unless n is exactly a tile width (8, 16, 32), where no spare lane exists. */
+static int tip_in_scan(int n) { return !(n == 8 || n == 16 || n == 32); }
+
 /* One evaluation: FK scan, body Jacobian, se(3) log error, weighted residual r,
  * weighted task Jacobian Jr = W * Jlog6(X) * J_body.
- * (kinematics.rs:123-196, math.rs:40-203, objective.rs:7-110 -- restated.) */
+ * (kinematics.rs:123-196, math.rs:40-203, objective.rs:7-110 -- restated.)
+ * FK is evaluated IN THE TARGET'S FRAME: joint 0's origin is pre-multiplied by T_tgt^-1 (tgt_inv), so the scan
+ * yields X = T_tgt^-1 * T_ee directly; the body-frame Jacobian is invariant to the choice of world frame. */
 void twin_evaluate(const twin_chain* c, const twin_params* P, se3t tgt, const double* q, twin_eval* E) {
   int n = c->n;
-  se3t T[MAX_DOF], Tn[MAX_DOF];
+  int fold = tip_in_scan(n);
+  int m = fold ? n + 1 : n;
+  se3t T[MAX_DOF + 1], Tn[MAX_DOF + 1];
+  se3t tgt_inv;
+  tgt_inv.q = qt_conj(tgt.q);
+  tgt_inv.t = v3_neg(qt_rot(tgt_inv.q, tgt.t));
   for (int j = 0; j < n; j++) { /* lane j: local transform origin_j * motion_j(q_j) */
+    se3t O;
+    O.q = c->oq[j]; O.t = c->ot[j];
+    if (j == 0) O = se3_mul(tgt_inv, O);
     if (c->type[j] == 0) {
       double s, cs;
       tw_sincos(0.5 * q[j], &s, &cs);
       qt qa = {c->ax[j].x * s, c->ax[j].y * s, c->ax[j].z * s, cs};
-      T[j].q = qt_mul(c->oq[j], qa);
-      T[j].t = c->ot[j];
+      T[j].q = qt_mul(O.q, qa);
+      T[j].t = O.t;
     } else {
-      T[j].q = c->oq[j];
-      T[j].t = v3_add(c->ot[j], qt_rot(c->oq[j], v3_scale(c->ax[j], q[j])));
+      T[j].q = O.q;
+      T[j].t = v3_add(O.t, qt_rot(O.q, v3_scale(c->ax[j], q[j])));
     }
   }
-  for (int d = 1; d < n; d <<= 1) { /* Kogge-Stone inclusive scan over lanes */
-    for (int j = 0; j < n; j++) Tn[j] = (j >= d) ? se3_mul(T[j - d], T[j]) : T[j];
-    memcpy(T, Tn, sizeof(se3t) * n);
+  if (fold) T[n] = c->tip;
+  for (int d = 1; d < m; d <<= 1) { /* Kogge-Stone inclusive scan over lanes */
+    for (int j = 0; j < m; j++) Tn[j] = (j >= d) ? se3_mul(T[j - d], T[j]) : T[j];
+    memcpy(T, Tn, sizeof(se3t) * m);
   }
-  se3t ee = se3_mul(T[n - 1], c->tip);
-  E->ee = ee;
-  /* pose error X = T_tgt^-1 * T_ee */
-  qt xq = qt_mul(qt_conj(tgt.q), ee.q);
-  v3 xt = qt_rot_inv(tgt.q, v3_sub(ee.t, tgt.t));
+  se3t ee = fold ? T[n] : se3_mul(T[n - 1], c->tip);
+  E->ee = ee; /* == X = T_tgt^-1 * T_ee (objective.rs:48-49) */
+  qt xq = ee.q;
+  v3 xt = ee.t;
   /* so3 log + scalar coefficients (half-angle identities; Taylor below theta^2 <= 1e-6) */
   double qw = xq.w;
   v3 v = v3_make(xq.x, xq.y, xq.z);
@@ -287,13 +301,15 @@ int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const doub
     }
     for (int a = 0; a < 6; a++)
       for (int b = 0; b <= a; b++) {
-        for (int j = 0; j < n; j++) tmp[j] = m[j] * (Ec.Jr[j][a] * Ec.Jr[j][b]);
+        for (int j = 0; j < n; j++) tmp[j] = (m[j] * Ec.Jr[j][a]) * Ec.Jr[j][b];
         A[a][b] = tree_sum(tmp, n);
       }
     for (int a = 0; a < 6; a++) A[a][a] = A[a][a] + lambda;
     ldl6_solve(A, Ec.r, y);
     for (int j = 0; j < n; j++) {
-      double dq = -(m[j] * dot6(Ec.Jr[j], y));
+      double Jm[6];
+      for (int a = 0; a < 6; a++) Jm[a] = m[j] * Ec.Jr[j][a];
+      double dq = -dot6(Jm, y);
       qt_[j] = fmin(fmax(qc[j] + dq, c->lb[j]), c->ub[j]);
     }
   }
@@ -319,6 +335,7 @@ int twin_eval_c(const double* chain, int njoints, const double* ee_offset, const
   if (rc) return rc;
   twin_eval E;
   twin_evaluate(&c, P, se3_from_pose8(target), q, &E);
+  E.ee = se3_mul(se3_from_pose8(target), E.ee); /* back to the world frame for reporting */
   ee8[0] = E.ee.q.x; ee8[1] = E.ee.q.y; ee8[2] = E.ee.q.z; ee8[3] = E.ee.q.w;
   ee8[4] = E.ee.t.x; ee8[5] = E.ee.t.y; ee8[6] = E.ee.t.z; ee8[7] = 0;
   *f = E.f;
