@@ -489,6 +489,7 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
                          double* grad_out, void* stream) {
   if (!robot || !q) return fail(OPTIK_ERR_INVALID, "null argument");
   if ((f_out || grad_out) && !targets) return fail(OPTIK_ERR_INVALID, "objective outputs need targets");
+  if (memory == 1 && (((uintptr_t)jac_out | (uintptr_t)ee_out) & 15)) return fail(OPTIK_ERR_INVALID, "ee_out / jac_out must be 16-byte aligned");
   if (B == 0) return OPTIK_OK;
   std::unique_lock<std::mutex> lk(robot->mu);
   if (int rc = robot->ensure_gpu()) return rc;
