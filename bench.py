@@ -37,7 +37,8 @@ def workload_config(n_gpus, tile):
         "workload": "configs[1]: Panda 7-DOF, 65536 random-restart seeds to one target per GPU per step, "
                     "SolutionMode::Quality, tol_f=1e-6, max_time=0, fresh reachable target every step",
         "robot": ROBOT, "dof": 7, "seeds_per_gpu_per_step": SEEDS_PER_GPU, "targets_per_step": 1,
-        "tile_lanes_per_seed": tile,
+        "lanes_per_seed": tile, "layout": ("thread-per-seed kernel (solve_t1_kernel)" if tile == 1 else
+                                           f"tile kernel, {tile} lanes per seed (solve_kernel<{tile}>)" if tile else "cpu"),
         "solve_definition": "one restart attempt that converged (f<tol_f inside the joint limits, re-verified)",
         "l2": "flushed (256 MiB write) before every timed step; steps timed individually with CUDA events",
         "parallelism": f"restart-range sharding over {n_gpus} GPU(s); one NCCL all-gather of 11 doubles/rank/step "
@@ -311,13 +312,13 @@ def run_product(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world, tile or 8),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, tile or 1),
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step_median": float(np.median(e2e_times) * 1e3), "api": "Robot.ik_attempts(host numpy buffers, pinned) -> optik_gpu_ik_attempts (C ABI)"},
             "gpu_launches": (2 if world == 1 else 3) * K,
             "roofline": roof,
-            "roofline_solve": {"kernel": "solve_kernel", "bound": "fp64 issue / latency (not HBM)",
+            "roofline_solve": {"kernel": "solve_t1_kernel" if (tile or 1) == 1 else f"solve_kernel<{tile}>", "bound": "fp64 issue / latency (not HBM)",
                                "hbm_gbs": attempts * solve_bytes / (dev_ms * 1e-3) / 1e9,
                                "evals_per_s": evals / (dev_ms * 1e-3), "attempts_per_s": attempts / (dev_ms * 1e-3)},
             "cpu_baseline": cpu,

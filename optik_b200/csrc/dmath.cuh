@@ -104,19 +104,26 @@ DEV double datan_poly(double x) {  // |x| <= 7/16
   s2 = w * s2;
   return x - x * (s1 + s2);
 }
+// atan on [0,1], fdlibm breakpoints: t < 7/16: poly(t); t < 11/16: atan(1/2) + atan((2t-1)/(2+t)); else
+// pi/4 + atan((t-1)/(t+1)).  Written branch-free (selected constants) so that threads with different arguments do
+// not diverge; every select reproduces the branchy formulation bit for bit ((1*t-0)/(1+0*t) == t, 2*t == t+t,
+// 0 + (p + 0) == p for p >= 0), which is what the CPU twin evaluates.
 DEV double datan01(double t) {  // 0 <= t <= 1
-  if (t < 0.4375) return datan_poly(t);
-  if (t < 0.6875) {
-    const double u = (t + t - 1.0) / (2.0 + t);
-    return 4.63647609000806093515e-01 + (datan_poly(u) + 2.26987774529616870924e-17);
-  }
-  const double u = (t - 1.0) / (t + 1.0);
-  return 7.85398163397448278999e-01 + (datan_poly(u) + 3.06161699786838301793e-17);
+  const bool b1 = t < 0.4375, b2 = t < 0.6875;
+  const double a = (b1 || !b2) ? 1.0 : 2.0;   // numerator  a*t - b
+  const double b = b1 ? 0.0 : 1.0;
+  const double c = (b1 || !b2) ? 1.0 : 2.0;   // denominator c + d*t
+  const double d = b1 ? 0.0 : 1.0;
+  const double hi = b1 ? 0.0 : (b2 ? 4.63647609000806093515e-01 : 7.85398163397448278999e-01);
+  const double lo = b1 ? 0.0 : (b2 ? 2.26987774529616870924e-17 : 3.06161699786838301793e-17);
+  const double u = (a * t - b) / (c + d * t);
+  return hi + (datan_poly(u) + lo);
 }
 // atan2(y, x) for y >= 0, x >= 0 (not both zero)
 DEV double datan2_pos(double y, double x) {
-  if (y <= x) return datan01(y / x);
-  return 1.57079632679489655800e+00 - (datan01(x / y) - 6.12323399573676603587e-17);
+  const bool small = y <= x;
+  const double a = datan01(small ? y / x : x / y);
+  return small ? a : 1.57079632679489655800e+00 - (a - 6.12323399573676603587e-17);
 }
 
 // ---- ChaCha8 block (integer; restates rand_chacha's ChaCha8Rng state layout:

@@ -28,6 +28,8 @@ extern "C" int optik_launch_select(const SelectParams* p, void* stream);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n);
+extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
+extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm);
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
 
 namespace {
@@ -129,6 +131,7 @@ struct optik_robot {
   mutable uint32_t chain_bytes = 0;
   mutable int sm_count = 0;
   mutable int occ[3] = {0, 0, 0};  // resident blocks/SM for TILE 8,16,32
+  mutable int occ_t1 = 0;          // resident blocks/SM of the thread-per-seed kernel (n <= 8)
   mutable DevBuf scratch;          // single-call scratch (ik / fk / jacobian), guarded by mu
   mutable cudaStream_t stream = nullptr;
   mutable void* pinned = nullptr;
@@ -192,6 +195,7 @@ struct optik_robot {
     sm_count = prop.multiProcessorCount;
     const int tiles[3] = {8, 16, 32};
     for (int i = 0; i < 3; i++) CUDA_TRY(optik_solve_occupancy(tiles[i], &occ[i]));
+    if (n <= 8) CUDA_TRY(optik_solve_t1_occupancy(n, &occ_t1));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     // keep stream-ordered scratch cached across synchronisations (the default threshold of 0 returns it to the
     // driver at every sync, which turns each host-path call into a fresh cudaMalloc)
@@ -227,8 +231,13 @@ optik_robot* try_from_urdf_str(const char* urdf, const char* base, const char* e
 struct Plan {
   int tile, blocks, tiles_per_block, resident_tiles;
 };
-int choose_tile(int n, uint32_t want) {
+// lanes per restart seed: 1 = thread-per-seed kernel (n <= 8), 8/16/32 = tile kernel.  `batch`: auto picks the
+// throughput layout (1) when it exists, otherwise / for single-target latency the smallest tile that fits.
+int choose_tile(int n, uint32_t want, bool batch) {
+  if (want == 1) return n <= 8 ? 1 : 0;
   if (want == 8 || want == 16 || want == 32) return (int)want >= n ? (int)want : 0;
+  if (want != 0) return 0;
+  if (batch && n <= 8) return 1;
   return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 }
 Plan make_plan(const optik_robot* r, int tile, uint32_t blocks_req, unsigned long long njobs) {
@@ -236,7 +245,8 @@ Plan make_plan(const optik_robot* r, int tile, uint32_t blocks_req, unsigned lon
   p.tile = tile;
   p.tiles_per_block = 128 / tile;
   const int oi = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
-  const int per_sm = r->occ[oi] > 0 ? r->occ[oi] : 1;
+  int per_sm = r->occ[oi] > 0 ? r->occ[oi] : 1;
+  if (tile == 1) per_sm = r->occ_t1 > 0 ? r->occ_t1 : 1;
   const long long resident_blocks = (long long)r->sm_count * per_sm;  // one full wave: a multiple of the SM count
   p.resident_tiles = (int)(resident_blocks * p.tiles_per_block);
   long long need = (long long)((njobs + p.tiles_per_block - 1) / p.tiles_per_block);
@@ -282,8 +292,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
                  const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
                  double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
                  unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
-  const int tile = choose_tile(r->n, o ? o->tile : 0);
-  if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 8, 16 or 32 and >= num_positions");
+  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
+  if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (num_positions <= 8), 8, 16 or 32 and >= num_positions");
   SolveParams P{};
   fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
   P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
@@ -317,6 +327,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const size_t off_ev = (direct && d_evals) ? 0 : carve(njobs * sizeof(int));
   const bool use_found = (cfg->solution_mode == OPTIK_MODE_SPEED) && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
+  const size_t off_queue = carve(sizeof(unsigned long long));
   char* scratch = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, s));
   P.cand_q = direct ? d_q : (double*)(scratch + off_q);
@@ -325,12 +336,15 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   P.cand_score = (double*)(scratch + off_score);
   P.cand_restart = restart_direct ? (unsigned long long*)d_restart : (unsigned long long*)(scratch + off_rs);
   P.cand_evals = (direct && d_evals) ? d_evals : (int*)(scratch + off_ev);
+  P.queue = (unsigned long long*)(scratch + off_queue);
+  CUDA_TRY(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), s));
   P.found = nullptr;
   if (use_found) {
     P.found = (unsigned long long*)(scratch + off_found);
     CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
   }
-  CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
+  if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, plan.blocks, s));
+  else CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
   if (per_attempt_records && d_best_record) {  // selection pass over the per-attempt records -> one packed record
     SelectParams S{};
     S.T = 1; S.C = P.C; S.n = n; S.mode = cfg->solution_mode;
@@ -649,7 +663,7 @@ static int ik_single(const optik_robot* robot, const optik_solver_config* config
   if (int rc = robot->ensure_gpu()) return -rc;
   if (cudaSetDevice(robot->device) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t s = robot->stream;
-  const int tile = choose_tile(n, 0);
+  const int tile = choose_tile(n, 0, false);  // single target: the low-latency tile layout
   const Plan plan = make_plan(robot, tile, 0, ~0ull);
   const uint64_t wave = (uint64_t)plan.resident_tiles;                                    // restarts per launch
   const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
@@ -670,6 +684,7 @@ static int ik_single(const optik_robot* robot, const optik_solver_config* config
   optik_gpu_batch_opts o{};
   o.struct_size = sizeof(o);
   o.memory = 1;
+  o.tile = (uint32_t)tile;
   o.ee_offset = ee_offset;
   bool have_best = false;
   double best_score = 0;

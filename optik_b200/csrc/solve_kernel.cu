@@ -19,7 +19,7 @@
 // Tensor cores are deliberately unused: 6 x n is not a dense contraction.
 #include <cuda_runtime.h>
 
-#include "dmath.cuh"
+#include "ik_math.cuh"
 #include "solver_params.h"
 
 #ifndef OPTIK_SOLVE_MIN_BLOCKS
@@ -27,31 +27,6 @@
 #endif
 
 namespace optik {
-
-// ------------------------------------------------------------------ TMA staging
-DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-DEV void stage_chain_tma(double* s_chain, uint64_t* s_bar, const double* g_chain, uint32_t bytes) {
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(s_chain)),
-                 "l"(g_chain), "r"(bytes), "r"(smem_u32(s_bar))
-                 : "memory");
-  }
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(s_bar)), "r"(0u)
-        : "memory");
-  } while (!ok);
-}
 
 // ------------------------------------------------------------------ tile collectives
 constexpr unsigned FULL = 0xffffffffu;
@@ -93,12 +68,6 @@ struct Joint {
   double lb, ub;
   int type;  // 0 revolute, 1 prismatic, 2 fixed transform (tip lane / padding lane)
 };
-DEV se3 load_pose8(const double* p) {
-  se3 r;
-  r.q.x = p[0]; r.q.y = p[1]; r.q.z = p[2]; r.q.w = p[3];
-  r.t = mk3(p[4], p[5], p[6]);
-  return r;
-}
 // tip handling rule (depends on n only, so every tile width gives the same bits): the fixed tip transform rides
 // the scan in lane n unless n is exactly a tile width (8, 16, 32), where no spare lane exists.
 DEV bool tip_in_scan(int n) { return !(n == 8 || n == 16 || n == 32); }
@@ -122,12 +91,6 @@ DEV Joint load_joint(const double* s_chain, const se3& tip, int lane, int n) {
   }
   return J;
 }
-DEV v3 weight3(qt tq, const double* w, v3 u) {  // R_tgt^T diag(w) R_tgt u   (objective.rs:13-35)
-  v3 a = qrot(tq, u);
-  a = mk3(a.x * w[0], a.y * w[1], a.z * w[2]);
-  return qrot_inv(tq, a);
-}
-
 // ------------------------------------------------------------------ one objective evaluation (all lanes)
 // Restates kinematics.rs:123-196 (FK scan, body Jacobian), math.rs:40-203 (so3/se3 log, d-log), objective.rs:7-110
 // (residual, weights, task Jacobian).  Outputs: f and r[6] (tile-uniform), Jr[6] (this lane's task-Jacobian column).
@@ -167,59 +130,25 @@ DEV void evaluate(const Joint& J, const se3& O, const double* s_tip, const doubl
   se3 ee = shfl_se3<TILE>(T, m - 1);
   if (!fold) ee = se3mul(ee, load_pose8(s_tip));
   // pose error X == ee (target frame)
-  double qw = ee.q.w;
-  v3 v = mk3(ee.q.x, ee.q.y, ee.q.z);
-  const v3 xt = ee.t;
-  if (!(qw >= 0.0)) { qw = -qw; v = neg3(v); }  // double cover, math.rs:43-47
-  const double vn2 = dot3(v, v);
-  double k, th2, ce, bq;
-  if (vn2 > 1e-6) {
-    const double vn = sqrt(vn2);
-    const double half = datan2_pos(vn, qw);
-    const double inv_vn = 1.0 / vn, inv_half = 1.0 / half;
-    k = half * inv_vn;
-    const double p = k * qw;  // (theta/2)/tan(theta/2)  == 1/2 theta sin/(1-cos), math.rs:112-114
-    const double it2 = 0.25 * (inv_half * inv_half);
-    th2 = 4.0 * (half * half);
-    ce = (1.0 - p) * it2;  // hat(w)^2 coefficient of V^-1 (math.rs:120-121), of J (math.rs:90-93) and a_q (math.rs:150)
-    const double a = (vn * qw) * inv_half;  // sin(theta)/theta
-    bq = fma((1.0 + a) * it2, 0.25 * (inv_vn * inv_vn), -2.0 * (it2 * it2));  // math.rs:151
-  } else {  // Taylor branches, math.rs:55-60, 115-118, 153-158
-    const double iw = 1.0 / qw, iw2 = iw * iw;
-    k = iw * fma(vn2 * iw2, fma(vn2 * iw2, 0.2, -1.0 / 3.0), 1.0);
-    th2 = 4.0 * ((k * k) * vn2);
-    ce = fma(th2, fma(th2, 1.0 / 30240.0, 1.0 / 720.0), 1.0 / 12.0);
-    bq = fma(th2, 1.0 / 7560.0, 1.0 / 360.0);
-  }
-  const v3 w = scale3(v, k + k);
-  const v3 wxt = cross3(w, xt);
-  const v3 elin = axpy3(ce, cross3(w, wxt), axpy3(-0.5, wxt, xt));  // V^-1 t
-  v3 rl = elin, ra = w;
+  ErrCoef ec;
+  v3 elin;
+  error_terms(ee.q, ee.t, ec, elin);
+  v3 rl = elin, ra = ec.w;
   qt tq;
   if (weighted) {
     tq.x = tgt_q[0]; tq.y = tgt_q[1]; tq.z = tgt_q[2]; tq.w = tgt_q[3];
-    rl = weight3(tq, wl, elin); ra = weight3(tq, wa, w);
+    rl = weight3(tq, wl, elin); ra = weight3(tq, wa, ec.w);
   }
   r[0] = rl.x; r[1] = rl.y; r[2] = rl.z; r[3] = ra.x; r[4] = ra.y; r[5] = ra.z;
   f = dot6(r, r);
-  // Q = C*J scalars (math.rs:160-169)
-  const double d = dot3(w, xt);
-  const double kc = fma(th2, bq, ce + ce);
-  const v3 cv = axpy3(bq * d, w, scale3(xt, -kc));
-  const double da = d * ce;
   // this lane's body-Jacobian column (kinematics.rs:171-193) -> task column Jlog6 * col (objective.rs:79-81)
   const v3 axw = qrot(T.q, J.ax);
   const v3 lw = cross3(axw, sub3(ee.t, T.t));
   v3 lin = qrot_inv(ee.q, lw);
   v3 ang = qrot_inv(ee.q, axw);
   if (has_prismatic && J.type == 1) { lin = ang; ang = mk3(0, 0, 0); }
-  const v3 wxa = cross3(w, ang);
-  const v3 ja = axpy3(ce, cross3(w, wxa), axpy3(0.5, wxa, ang));
-  const v3 wxl = cross3(w, lin);
-  const v3 jl = axpy3(ce, cross3(w, wxl), axpy3(0.5, wxl, lin));
-  const double wu = dot3(w, ja), tu = dot3(xt, ja);
-  const v3 cu = axpy3(da, ja, axpy3(ce * tu, w, axpy3(wu, cv, scale3(cross3(xt, ja), 0.5))));
-  v3 top = add3(jl, cu), bot = ja;
+  v3 top, bot;
+  task_col(ec, lin, ang, top, bot);
   if (weighted) { top = weight3(tq, wl, top); bot = weight3(tq, wa, bot); }
   const bool live = (J.type != 2);
   Jr[0] = live ? top.x : 0.0; Jr[1] = live ? top.y : 0.0; Jr[2] = live ? top.z : 0.0;
@@ -227,12 +156,6 @@ DEV void evaluate(const Joint& J, const se3& O, const double* s_tip, const doubl
 }
 
 #include "ldl6.cuh"
-
-DEV unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // ------------------------------------------------------------------ the solve kernel
 template <int TILE>
@@ -244,8 +167,6 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
 
   const int n = P.n;
   const int lane = threadIdx.x % TILE;
-  const unsigned tiles_per_block = blockDim.x / TILE;
-  const unsigned long long total_tiles = (unsigned long long)tiles_per_block * gridDim.x;
   const unsigned long long njobs = P.T * (unsigned long long)P.C;
   if (threadIdx.x == 0) {  // tip = fixed tip joint * ee_offset, once per block
     const se3 tip = se3mul(load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), load_pose8(P.ee_offset));
@@ -258,7 +179,9 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
   const unsigned long long t_start = P.max_ns ? globaltimer_ns() : 0ull;
 
   // ---- tile state (uniform across the tile unless marked "lane")
-  unsigned long long job = (unsigned long long)blockIdx.x * tiles_per_block + threadIdx.x / TILE;
+  unsigned long long job = 0;
+  // lanes of this tile (shuffles inside the divergent transition code name exactly the tile's lanes)
+  const unsigned tile_mask = (TILE == 32) ? 0xffffffffu : (((1u << (TILE & 31)) - 1u) << (((threadIdx.x & 31) / TILE) * TILE));
   unsigned long long tgt_id = 0, r_idx = 0;
   bool need_job = true, running = false, done = false, best_has = false;
   se3 O;                          // lane: this lane's origin (lane 0: pre-multiplied by T_tgt^-1 per job)
@@ -275,6 +198,9 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
     if (!running && !done) {
       for (;;) {
         if (need_job) {
+          unsigned long long next = 0;
+          if (lane == 0) next = atomicAdd(P.queue, 1ull);  // dynamic job queue, one fetch per tile
+          job = __shfl_sync(tile_mask, next, 0, TILE);
           if (job >= njobs) { done = true; break; }
           tgt_id = job / P.C;
           r_idx = P.r_begin + job % P.C;
@@ -311,7 +237,6 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
           break;
         }
         if (lane == 0) P.cand_evals[job] = job_evals;  // job finished
-        job += total_tiles;
         need_job = true;
       }
     }

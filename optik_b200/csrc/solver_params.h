@@ -60,6 +60,7 @@ struct SolveParams {
   // Speed-mode early exit: per-target lowest converged restart index so far (init ~0ull), or null
   unsigned long long* found;
   unsigned long long max_ns;  // 0 = no deadline; else nanoseconds from kernel start
+  unsigned long long* queue;  // job queue head (zeroed before launch): idle tiles/threads pull the next (target, chunk) job
   // candidate records, one per (target, chunk): [T*C]
   double* cand_q;                     // [T*C][n]
   double* cand_f;                     // objective value of the recorded attempt

@@ -43,6 +43,7 @@ typedef struct twin_params {
   double lambda0, lambda_dec, lambda_inc, lambda_min, lambda_max;
   double stall_rel; /* accepted step with df < stall_rel*f counts as "slow" */
   int stall_count;  /* this many consecutive slow steps => ST_STUCK */
+  int layout;       /* 0: tile (lane per joint) kernel, 1: thread-per-seed kernel -- different summation orders */
 } twin_params;
 
 typedef struct twin_chain {
@@ -113,6 +114,58 @@ static inline v3 weight3(qt tq, const double w[3], v3 u) {
   return qt_rot_inv(tq, a);
 }
 
+/* Pose-error terms shared by both kernel layouts: X = (xq, xt) -> w = so3 log, elin = V^-1 t, and the scalars of
+ * Jlog6 (math.rs:40-203 restated with half-angle identities; Taylor below theta^2 <= 1e-6). */
+typedef struct { v3 w, xt, cv; double ce, da; } err_coef;
+static void error_terms(qt xq, v3 xt, err_coef* c, v3* elin) {
+  double qw = xq.w;
+  v3 v = v3_make(xq.x, xq.y, xq.z);
+  if (!(qw >= 0.0)) { qw = -qw; v = v3_neg(v); }
+  double vn2 = v3_dot(v, v), k, th2, ce, bq;
+  if (vn2 > 1e-6) {
+    double vn = sqrt(vn2);
+    double half = tw_atan2_pos(vn, qw);
+    double inv_vn = 1.0 / vn, inv_half = 1.0 / half;
+    k = half * inv_vn;                         /* atan2(|v|,w)/|v| */
+    double p = k * qw;                         /* (theta/2)/tan(theta/2) */
+    double it2 = 0.25 * (inv_half * inv_half); /* 1/theta^2 */
+    th2 = 4.0 * (half * half);
+    ce = (1.0 - p) * it2;                      /* coefficient of hat(w)^2 in V^-1, J and a_q of Q */
+    double a = (vn * qw) * inv_half;           /* sin(theta)/theta */
+    bq = fma((1.0 + a) * it2, 0.25 * (inv_vn * inv_vn), -2.0 * (it2 * it2));
+  } else {
+    double iw = 1.0 / qw, iw2 = iw * iw;
+    k = iw * fma(vn2 * iw2, fma(vn2 * iw2, 0.2, -1.0 / 3.0), 1.0);
+    th2 = 4.0 * ((k * k) * vn2);
+    ce = fma(th2, fma(th2, 1.0 / 30240.0, 1.0 / 720.0), 1.0 / 12.0);
+    bq = fma(th2, 1.0 / 7560.0, 1.0 / 360.0);
+  }
+  v3 w = v3_scale(v, k + k);
+  /* e = [V^-1 t ; w],  V^-1 u = u - 1/2 w x u + ce w x (w x u) */
+  v3 wxt = v3_cross(w, xt);
+  *elin = v3_axpy(ce, v3_cross(w, wxt), v3_axpy(-0.5, wxt, xt));
+  /* Q = C*J scalars */
+  double d = v3_dot(w, xt);
+  double kc = fma(th2, bq, ce + ce);
+  c->w = w; c->xt = xt; c->ce = ce;
+  c->cv = v3_axpy(bq * d, w, v3_scale(xt, -kc)); /* b d w - (theta^2 b + 2a) t */
+  c->da = d * ce;
+}
+/* task column = Jlog6 * [lin; ang]:  top = J lin + C (J ang), bot = J ang */
+static void task_col(const err_coef* c, v3 lin, v3 ang, v3* top, v3* bot) {
+  v3 w = c->w;
+  /* J u = u + 1/2 w x u + ce w x (w x u) */
+  v3 wxa = v3_cross(w, ang);
+  v3 ja = v3_axpy(c->ce, v3_cross(w, wxa), v3_axpy(0.5, wxa, ang));
+  v3 wxl = v3_cross(w, lin);
+  v3 jl = v3_axpy(c->ce, v3_cross(w, wxl), v3_axpy(0.5, wxl, lin));
+  /* C u = 1/2 t x u + cv (w.u) + ce w (t.u) + d ce u */
+  double wu = v3_dot(w, ja), tu = v3_dot(c->xt, ja);
+  v3 cu = v3_axpy(c->da, ja, v3_axpy(c->ce * tu, w, v3_axpy(wu, c->cv, v3_scale(v3_cross(c->xt, ja), 0.5))));
+  *top = v3_add(jl, cu);
+  *bot = ja;
+}
+
 /* tip handling rule (depends on n only, so every tile width gives the same bits): the fixed tip transform rides
  * the scan as entry n unless n is exactly a tile width (8, 16, 32), where no spare lane exists. */
 static int tip_in_scan(int n) { return !(n == 8 || n == 16 || n == 32); }
@@ -154,42 +207,13 @@ void twin_evaluate(const twin_chain* c, const twin_params* P, se3t tgt, const do
   E->ee = ee; /* == X = T_tgt^-1 * T_ee (objective.rs:48-49) */
   qt xq = ee.q;
   v3 xt = ee.t;
-  /* so3 log + scalar coefficients (half-angle identities; Taylor below theta^2 <= 1e-6) */
-  double qw = xq.w;
-  v3 v = v3_make(xq.x, xq.y, xq.z);
-  if (!(qw >= 0.0)) { qw = -qw; v = v3_neg(v); }
-  double vn2 = v3_dot(v, v), k, th2, ce, bq;
-  if (vn2 > 1e-6) {
-    double vn = sqrt(vn2);
-    double half = tw_atan2_pos(vn, qw);
-    double inv_vn = 1.0 / vn, inv_half = 1.0 / half;
-    k = half * inv_vn;                       /* atan2(|v|,w)/|v| */
-    double p = k * qw;                       /* (theta/2)/tan(theta/2) */
-    double it2 = 0.25 * (inv_half * inv_half); /* 1/theta^2 */
-    th2 = 4.0 * (half * half);
-    ce = (1.0 - p) * it2;                    /* coefficient of hat(w)^2 in V^-1, J and a_q of Q */
-    double a = (vn * qw) * inv_half;         /* sin(theta)/theta */
-    bq = fma((1.0 + a) * it2, 0.25 * (inv_vn * inv_vn), -2.0 * (it2 * it2));
-  } else {
-    double iw = 1.0 / qw, iw2 = iw * iw;
-    k = iw * fma(vn2 * iw2, fma(vn2 * iw2, 0.2, -1.0 / 3.0), 1.0);
-    th2 = 4.0 * ((k * k) * vn2);
-    ce = fma(th2, fma(th2, 1.0 / 30240.0, 1.0 / 720.0), 1.0 / 12.0);
-    bq = fma(th2, 1.0 / 7560.0, 1.0 / 360.0);
-  }
-  v3 w = v3_scale(v, k + k);
-  /* e = [V^-1 t ; w],  V^-1 u = u - 1/2 w x u + ce w x (w x u) */
-  v3 wxt = v3_cross(w, xt);
-  v3 elin = v3_axpy(ce, v3_cross(w, wxt), v3_axpy(-0.5, wxt, xt));
-  v3 rl = elin, ra = w;
-  if (P->weighted) { rl = weight3(tgt.q, P->wl, elin); ra = weight3(tgt.q, P->wa, w); }
+  err_coef ec;
+  v3 elin;
+  error_terms(xq, xt, &ec, &elin);
+  v3 rl = elin, ra = ec.w;
+  if (P->weighted) { rl = weight3(tgt.q, P->wl, elin); ra = weight3(tgt.q, P->wa, ec.w); }
   E->r[0] = rl.x; E->r[1] = rl.y; E->r[2] = rl.z; E->r[3] = ra.x; E->r[4] = ra.y; E->r[5] = ra.z;
   E->f = dot6(E->r, E->r);
-  /* Q = C*J scalars */
-  double d = v3_dot(w, xt);
-  double kc = fma(th2, bq, ce + ce);
-  v3 cv = v3_axpy(bq * d, w, v3_scale(xt, -kc)); /* b d w - (theta^2 b + 2a) t */
-  double da = d * ce;
   for (int j = 0; j < n; j++) { /* lane j: body Jacobian column -> task column */
     v3 lin, ang;
     v3 axw = qt_rot(T[j].q, c->ax[j]);
@@ -201,15 +225,8 @@ void twin_evaluate(const twin_chain* c, const twin_params* P, se3t tgt, const do
       lin = qt_rot_inv(ee.q, axw);
       ang = v3_make(0, 0, 0);
     }
-    /* J u = u + 1/2 w x u + ce w x (w x u) */
-    v3 wxa = v3_cross(w, ang);
-    v3 ja = v3_axpy(ce, v3_cross(w, wxa), v3_axpy(0.5, wxa, ang));
-    v3 wxl = v3_cross(w, lin);
-    v3 jl = v3_axpy(ce, v3_cross(w, wxl), v3_axpy(0.5, wxl, lin));
-    /* C u = 1/2 t x u + cv (w.u) + ce w (t.u) + d ce u */
-    double wu = v3_dot(w, ja), tu = v3_dot(xt, ja);
-    v3 cu = v3_axpy(da, ja, v3_axpy(ce * tu, w, v3_axpy(wu, cv, v3_scale(v3_cross(xt, ja), 0.5))));
-    v3 top = v3_add(jl, cu), bot = ja;
+    v3 top, bot;
+    task_col(&ec, lin, ang, &top, &bot);
     if (P->weighted) { top = weight3(tgt.q, P->wl, top); bot = weight3(tgt.q, P->wa, bot); }
     E->Jr[j][0] = top.x; E->Jr[j][1] = top.y; E->Jr[j][2] = top.z;
     E->Jr[j][3] = bot.x; E->Jr[j][4] = bot.y; E->Jr[j][5] = bot.z;
@@ -259,8 +276,11 @@ int twin_trace_cap = 0;
 void twin_set_trace(double* buf, int cap) { twin_trace = buf; twin_trace_cap = cap; }
 
 /* One restart attempt from q_init. Returns status; q_out/f_out = last trial point on exit. */
+static int twin_attempt_t1(const twin_chain* c, const twin_params* P, se3t tgt, const double* q_init, double* q_out,
+                           double* f_out, int* evals_out);
 int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const double* q_init, double* q_out,
                  double* f_out, int* evals_out) {
+  if (P->layout == 1) return twin_attempt_t1(c, P, tgt, q_init, q_out, f_out, evals_out);
   int n = c->n, evals = 0, have_cur = 0, status = ST_NONE, slow = 0;
   double qc[MAX_DOF], qt_[MAX_DOF], lambda = P->lambda0;
   twin_eval Ec, Et;
@@ -315,6 +335,118 @@ int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const doub
   }
   memcpy(q_out, qt_, sizeof(double) * n);
   *f_out = Et.f;
+  *evals_out = evals;
+  return status;
+}
+
+/* ======================= layout 1: thread-per-seed kernel (solve_t1_kernel.cu) =======================
+ * Same objective, stop rules and LM step; sequential instead of lane-parallel evaluation order:
+ *   - one BACKWARD recursion B_{j-1} = L_j B_j (B_n = tip) in the target's frame yields X = B_0 and, on the way,
+ *     the body-Jacobian column of joint j from B_j:  [R_Bj^T (a_j x p_Bj) ; R_Bj^T a_j]
+ *   - Gram matrix and score are accumulated joint by joint with fma (no tree). */
+static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, const double* q, double* f, double* r,
+                         double body[][6], err_coef* ec) {
+  int n = c->n;
+  se3t tgt_inv;
+  tgt_inv.q = qt_conj(tgt.q);
+  tgt_inv.t = v3_neg(qt_rot(tgt_inv.q, tgt.t));
+  se3t B = c->tip;
+  for (int j = n - 1; j >= 0; j--) {
+    v3 ax = c->ax[j];
+    if (c->type[j] == 0) {
+      v3 lin = qt_rot_inv(B.q, v3_cross(ax, B.t)), ang = qt_rot_inv(B.q, ax);
+      body[j][0] = lin.x; body[j][1] = lin.y; body[j][2] = lin.z; body[j][3] = ang.x; body[j][4] = ang.y; body[j][5] = ang.z;
+    } else {
+      v3 lin = qt_rot_inv(B.q, ax);
+      body[j][0] = lin.x; body[j][1] = lin.y; body[j][2] = lin.z; body[j][3] = 0; body[j][4] = 0; body[j][5] = 0;
+    }
+    se3t O, L;
+    O.q = c->oq[j]; O.t = c->ot[j];
+    if (j == 0) O = se3_mul(tgt_inv, O);
+    if (c->type[j] == 0) {
+      double s, cs;
+      tw_sincos(0.5 * q[j], &s, &cs);
+      qt qa = {ax.x * s, ax.y * s, ax.z * s, cs};
+      L.q = qt_mul(O.q, qa);
+      L.t = O.t;
+    } else {
+      L.q = O.q;
+      L.t = v3_add(O.t, qt_rot(O.q, v3_scale(ax, q[j])));
+    }
+    B = se3_mul(L, B);
+  }
+  v3 elin;
+  error_terms(B.q, B.t, ec, &elin);
+  v3 rl = elin, ra = ec->w;
+  if (P->weighted) { rl = weight3(tgt.q, P->wl, elin); ra = weight3(tgt.q, P->wa, ec->w); }
+  r[0] = rl.x; r[1] = rl.y; r[2] = rl.z; r[3] = ra.x; r[4] = ra.y; r[5] = ra.z;
+  *f = dot6(r, r);
+}
+
+static int twin_attempt_t1(const twin_chain* c, const twin_params* P, se3t tgt, const double* q_init, double* q_out,
+                           double* f_out, int* evals_out) {
+  int n = c->n, evals = 0, have_cur = 0, status = ST_NONE, slow = 0;
+  double qc[MAX_DOF], qt_[MAX_DOF], lambda = P->lambda0, fc = 0, ft, rc[6], rt[6];
+  double body[MAX_DOF][6], C[MAX_DOF][6];
+  err_coef ec;
+  for (int j = 0; j < n; j++) qt_[j] = fmin(fmax(q_init[j], c->lb[j]), c->ub[j]);
+  for (;;) {
+    twin_eval_t1(c, P, tgt, qt_, &ft, rt, body, &ec);
+    evals++;
+    int accept = 0;
+    if (ft != ft) status = ST_NAN;
+    else if (ft < P->tol_f) status = ST_STOPVAL;
+    else if (!have_cur) accept = 1;
+    else if (ft < fc) {
+      accept = 1;
+      double df = fc - ft, dx = 0;
+      for (int j = 0; j < n; j++) dx = fmax(dx, fabs(qt_[j] - qc[j]));
+      if (df < P->tol_df_eff) status = ST_FTOL;
+      else if (P->tol_dx > 0.0 && dx < P->tol_dx) status = ST_XTOL;
+      slow = (df < P->stall_rel * fc) ? slow + 1 : 0;
+      if (status == ST_NONE && slow >= P->stall_count) status = ST_STUCK;
+      lambda = fmax(lambda * P->lambda_dec, P->lambda_min);
+    } else {
+      lambda = lambda * P->lambda_inc;
+      if (lambda > P->lambda_max) status = ST_STUCK;
+    }
+    if (twin_trace && evals <= twin_trace_cap) {
+      twin_trace[3 * (evals - 1)] = ft; twin_trace[3 * (evals - 1) + 1] = lambda; twin_trace[3 * (evals - 1) + 2] = accept;
+    }
+    if (status == ST_NONE && evals >= P->max_evals) status = ST_ITERCAP;
+    if (status != ST_NONE) break;
+    if (accept) { /* current point <- trial: task columns from the trial's body columns */
+      memcpy(qc, qt_, sizeof(double) * n);
+      memcpy(rc, rt, sizeof(rc));
+      fc = ft; have_cur = 1;
+      for (int j = 0; j < n; j++) {
+        v3 top, bot;
+        task_col(&ec, v3_make(body[j][0], body[j][1], body[j][2]), v3_make(body[j][3], body[j][4], body[j][5]), &top, &bot);
+        if (P->weighted) { top = weight3(tgt.q, P->wl, top); bot = weight3(tgt.q, P->wa, bot); }
+        C[j][0] = top.x; C[j][1] = top.y; C[j][2] = top.z; C[j][3] = bot.x; C[j][4] = bot.y; C[j][5] = bot.z;
+      }
+    }
+    double A[6][6], y[6], m[MAX_DOF];
+    for (int a = 0; a < 6; a++) for (int b = 0; b <= a; b++) A[a][b] = 0.0;
+    for (int j = 0; j < n; j++) {
+      double g = dot6(rc, C[j]);
+      int pinned = (qc[j] <= c->lb[j] && g > 0.0) || (qc[j] >= c->ub[j] && g < 0.0);
+      m[j] = pinned ? 0.0 : 1.0;
+      for (int a = 0; a < 6; a++) {
+        double jm = m[j] * C[j][a];
+        for (int b = 0; b <= a; b++) A[a][b] = fma(jm, C[j][b], A[a][b]);
+      }
+    }
+    for (int a = 0; a < 6; a++) A[a][a] = A[a][a] + lambda;
+    ldl6_solve(A, rc, y);
+    for (int j = 0; j < n; j++) {
+      double Jm[6];
+      for (int a = 0; a < 6; a++) Jm[a] = m[j] * C[j][a];
+      qt_[j] = fmin(fmax(qc[j] - dot6(Jm, y), c->lb[j]), c->ub[j]);
+    }
+  }
+  memcpy(q_out, qt_, sizeof(double) * n);
+  *f_out = ft;
   *evals_out = evals;
   return status;
 }
@@ -389,8 +521,12 @@ int twin_ik_c(const double* chain, int njoints, const double* ee_offset, const t
     if (ok) {
       double score = 0.0;
       if (mode == 1) {
-        for (int j = 0; j < c.n; j++) { double d = q[j] - x0[j]; d2[j] = d * d; }
-        score = tree_sum(d2, c.n);
+        if (P->layout == 1) {
+          for (int j = 0; j < c.n; j++) { double d = q[j] - x0[j]; score = fma(d, d, score); }
+        } else {
+          for (int j = 0; j < c.n; j++) { double d = q[j] - x0[j]; d2[j] = d * d; }
+          score = tree_sum(d2, c.n);
+        }
       }
       if (!have || score < best_score) {
         have = 1; best_score = score;

@@ -20,6 +20,11 @@ def robot_and_chain(name):
     return r, O.Chain(r.chain())
 
 
+def twin_layout(ch, tile=0):
+    """Which twin mirrors the kernel the library picks: thread-per-seed (1) for tile=1 or auto with n <= 8."""
+    return 1 if (tile == 1 or (tile == 0 and ch.n <= 8)) else 0
+
+
 def targets_for(ch, rng, T):
     out = np.zeros((T, 8))
     for t in range(T):
@@ -87,8 +92,9 @@ def test_evaluator_ee_offset_and_single_calls():
 
 
 # ------------------------------------------------------------------ solver vs twin, per restart seed
-@pytest.mark.parametrize("name,tile,R", [("panda", 8, 2048), ("panda", 32, 512), ("ur5", 8, 1024), ("ur5", 16, 256),
-                                          ("ur3e", 8, 512), ("snake20", 32, 512)])
+@pytest.mark.parametrize("name,tile,R", [("panda", 1, 4096), ("ur5", 1, 2048), ("ur3e", 1, 1024),
+                                          ("panda", 8, 2048), ("panda", 32, 512), ("ur5", 8, 1024), ("ur5", 16, 256),
+                                          ("ur3e", 8, 512), ("snake20", 32, 512), ("snake20", 0, 256), ("panda", 0, 512)])
 def test_attempts_match_twin_per_seed(name, tile, R):
     r, ch = robot_and_chain(name)
     rng = np.random.default_rng(42)
@@ -96,7 +102,7 @@ def test_attempts_match_twin_per_seed(name, tile, R):
     x0 = 0.5 * (ch.lb + ch.ub)
     cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
     q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R, tile=tile)
-    tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 0, R)
+    tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 0, R, O.twin_params(layout=twin_layout(ch, tile)))
     assert np.array_equal(st, tst), "success set / status differs from the CPU twin"
     assert np.array_equal(ev, tev)
     ok = st == 1
@@ -119,27 +125,31 @@ def test_attempts_with_weights_tolerances_and_offsets():
     tgt = ch.fk(rng.uniform(ch.lb, ch.ub), off)[1]
     for kw in (dict(tol_f=1e-12), dict(tol_df=1e-4), dict(tol_dx=1e-3), dict(linear_weight=[1.0, 2.0, 0.5], angular_weight=[0.1, 1.0, 1.0])):
         cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=128, **kw)
-        P = O.twin_params(tol_f=cfg.tol_f, tol_df=cfg.tol_df, tol_dx=cfg.tol_dx, wl=cfg.linear_weight, wa=cfg.angular_weight)
-        q, f, st, ev = r.ik_attempts(cfg, tgt, x0, 128, restart_begin=5, ee_offset=off)
-        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 5, 133, P, ee_offset=off)
-        assert np.array_equal(st, tst) and np.array_equal(ev, tev), kw
-        assert np.abs(q - tq).max() <= RAD_TOL, kw
-        assert cfg.is_success(st).sum() > 5, kw
+        for tile in (1, 8):
+            P = O.twin_params(tol_f=cfg.tol_f, tol_df=cfg.tol_df, tol_dx=cfg.tol_dx, wl=cfg.linear_weight,
+                              wa=cfg.angular_weight, layout=twin_layout(ch, tile))
+            q, f, st, ev = r.ik_attempts(cfg, tgt, x0, 128, restart_begin=5, ee_offset=off, tile=tile)
+            tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 5, 133, P, ee_offset=off)
+            assert np.array_equal(st, tst) and np.array_equal(ev, tev), (kw, tile)
+            assert np.abs(q - tq).max() <= RAD_TOL, (kw, tile)
+            assert cfg.is_success(st).sum() > 5, (kw, tile)
 
 
 # ------------------------------------------------------------------ batched ik(): selection semantics
 @pytest.mark.parametrize("mode", ["speed", "quality"])
 @pytest.mark.parametrize("chunks", [1, 4, 0])
-def test_ik_batch_matches_reference_selection(mode, chunks):
+@pytest.mark.parametrize("tile", [0, 8])
+def test_ik_batch_matches_reference_selection(mode, chunks, tile):
     r, ch = robot_and_chain("panda")
     rng = np.random.default_rng(7)
     T, R = 96, 12
     tg = targets_for(ch, rng, T)
     x0 = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
     cfg = ob.SolverConfig(solution_mode=mode, max_time=0.0, max_restarts=R)
-    q, f, st, extra = r.ik_batch(cfg, tg, x0, restarts=R, chunks=chunks, stats=True)
+    q, f, st, extra = r.ik_batch(cfg, tg, x0, restarts=R, chunks=chunks, tile=tile, stats=True)
+    P = O.twin_params(layout=twin_layout(ch, tile))
     for t in range(T):
-        ref = O.twin_ik(ch, tg[t], x0[t], 0, R, mode)
+        ref = O.twin_ik(ch, tg[t], x0[t], 0, R, mode, P)
         assert bool(cfg.is_success(st[t])) == ref["found"], t
         if ref["found"]:
             assert int(extra["restart"][t]) == ref["restart"], t
@@ -269,7 +279,7 @@ def test_config2_full_size_properties():
     assert np.all(q[ok] >= ch.lb) and np.all(q[ok] <= ch.ub)
     idx = rng.choice(R, 256, replace=False)
     for i in idx:
-        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1)
+        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1, O.twin_params(layout=twin_layout(ch)))
         assert tst[0] == st[i] and tev[0] == ev[i] and np.array_equal(tq[0], q[i])
     # Quality selection over all seeds == arg-min distance among converged
     qb, fb, sb = r.ik_batch(cfg, tgt[None, :], x0[None, :], restarts=R)
@@ -286,7 +296,7 @@ def test_attempts_best_record_matches_reference_selection(mode):
     x0 = rng.uniform(ch.lb, ch.ub)
     cfg = ob.SolverConfig(solution_mode=mode, max_time=0.0, max_restarts=300)
     q, f, st, ev, rec = r.ik_attempts(cfg, tgt, x0, 300, restart_begin=40, best=True)
-    ref = O.twin_ik(ch, tgt, x0, 40, 340, mode)
+    ref = O.twin_ik(ch, tgt, x0, 40, 340, mode, O.twin_params(layout=twin_layout(ch)))
     assert ref["found"] and rec[0] == 1.0
     assert int(rec[2]) == ref["restart"] and rec[4] == ref["status"] and rec[3] == ref["f"]
     assert np.array_equal(rec[8:], ref["q"])

@@ -28,10 +28,11 @@ def run(name, T, R, mode, tile, chunks=0, reps=3):
           f"attempts={cnt[0]} att/s={cnt[0]/best*1e3:.3e} evals/att={cnt[1]/max(cnt[0],1):.1f} evals/s={cnt[1]/best*1e3:.3e}")
 
 if __name__ == "__main__":
-    for tile in (8, 32):
+    for tile in (1, 8, 32):
         run("panda", 1, 65536, "quality", tile)
-    for tile in (8, 32):
+    run("panda", 1, 1048576, "quality", 1)
+    for tile in (1, 8):
         run("panda", 262144, 32, "speed", tile)
-    run("ur5", 1048576, 32, "speed", 8)
+    run("ur5", 1048576, 32, "speed", 1)
     run("snake20", 1, 262144, "quality", 32)
-    run("panda", 16384, 256, "quality", 8)
+    run("panda", 16384, 256, "quality", 1)
