@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
   // lanes of this tile (shuffles inside the divergent transition code name exactly the tile's lanes)
   const unsigned tile_mask = (TILE == 32) ? 0xffffffffu : (((1u << (TILE & 31)) - 1u) << (((threadIdx.x & 31) / TILE) * TILE));
   unsigned long long tgt_id = 0, r_idx = 0;
-  bool need_job = true, running = false, done = false, best_has = false;
+  bool need_job = true, running = false, done = false, best_has = false, rec_any = false;
   se3 O;                          // lane: this lane's origin (lane 0: pre-multiplied by T_tgt^-1 per job)
   O.q = J.oq; O.t = J.ot;
   double x0 = 0.0;                // lane
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
             o0.q = J.oq; o0.t = J.ot;
             O = se3mul(ti, o0);
           }
-          best_has = false; best_score = 0.0; job_evals = 0;
+          best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
           if (lane < n) P.cand_q[job * n + lane] = x0;  // record of a chunk that runs no attempt
           if (lane == 0) {
             P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_idx;
@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
     if (status != OPTIK_ST_NONE) {  // attempt over
       n_attempts++; n_evals += evals; job_evals += evals;
       // r_idx only grows within a chunk, so on score ties the lower index is kept
-      const bool record = success ? (!best_has || score < best_score) : !best_has;
+      const bool record = success ? (!best_has || score < best_score) : !rec_any;  // failures: keep the first
       if (record) {  // the chunk's candidate record lives in HBM, not in registers
+        rec_any = true;
         if (lane < n) P.cand_q[job * n + lane] = qt_;
         if (lane == 0) {
           P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
 
   // ---- per-thread state.  A "job" is one (target, chunk): restarts r_begin+c, +C, ... run in index order.
   unsigned long long job = 0, tgt_id = 0, r_idx = 0, nxt_job = 0, nxt_r = 0;
-  bool running = false, job_open = false, best_has = false, have_next = false, queue_done = false, done = false;
+  bool running = false, job_open = false, best_has = false, rec_any = false, have_next = false, queue_done = false, done = false;
   se3 O0;  // origin of joint 0 pre-multiplied by T_tgt^-1 (FK in the target's frame)
   O0.q.x = O0.q.y = O0.q.z = 0; O0.q.w = 1; O0.t = mk3(0, 0, 0);
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
           o0.q.x = s_chain[4]; o0.q.y = s_chain[5]; o0.q.z = s_chain[6]; o0.q.w = s_chain[7];
           o0.t = mk3(s_chain[0], s_chain[1], s_chain[2]);
           O0 = se3mul(ti, o0);
-          best_has = false; best_score = 0.0; job_evals = 0;
+          best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
           for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[tgt_id * n + j];  // record if no attempt runs
           P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = nxt_r;
           P.cand_status[job] = OPTIK_ST_SKIPPED;
@@ -259,8 +259,9 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
           score = fma(d, d, score);
         }
       n_attempts++; n_evals += evals; job_evals += evals;
-      const bool record = success ? (!best_has || score < best_score) : !best_has;
+      const bool record = success ? (!best_has || score < best_score) : !rec_any;  // failures: keep the first
       if (record) {
+        rec_any = true;
         for (int j = 0; j < n; j++) P.cand_q[job * n + j] = qt_[j * T1_THREADS];
         P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
       }

@@ -323,3 +323,127 @@ def test_select_records_kernel_matches_rule():
             assert torch.equal(got, want), count
         else:
             assert got[0] == 0.0
+
+
+# ------------------------------------------------------------------ chain shapes beyond the bundled robots
+def synth_urdf(joints, tip=None):
+    """joints: list of (type, xyz, rpy, axis, lo, hi)."""
+    s = ['<robot name="synth">', '<link name="l0"/>']
+    for i, (typ, xyz, rpy, axis, lo, hi) in enumerate(joints):
+        s.append(f'<link name="l{i+1}"/>')
+        s.append(f'<joint name="j{i}" type="{typ}"><parent link="l{i}"/><child link="l{i+1}"/>'
+                 f'<origin xyz="{xyz}" rpy="{rpy}"/><axis xyz="{axis}"/>'
+                 f'<limit lower="{lo}" upper="{hi}" effort="1" velocity="1"/></joint>')
+    last = f"l{len(joints)}"
+    if tip:
+        s.append('<link name="tip"/>')
+        s.append(f'<joint name="jt" type="fixed"><parent link="{last}"/><child link="tip"/><origin xyz="{tip[0]}" rpy="{tip[1]}"/></joint>')
+        last = "tip"
+    s.append("</robot>")
+    return "\n".join(s), "l0", last
+
+
+def arm(n, prismatic_at=(), tip=("0 0.05 0.1", "0.3 0 0.2")):
+    rng = np.random.default_rng(n)
+    js = []
+    for i in range(n):
+        axis = ["0 0 1", "0 1 0", "1 0 0", "0.6 0 0.8"][i % 4]
+        xyz = " ".join(f"{v:.3f}" for v in rng.uniform(-0.15, 0.25, 3))
+        rpy = " ".join(f"{v:.3f}" for v in rng.uniform(-1.0, 1.0, 3))
+        if i in prismatic_at:
+            js.append(("prismatic", xyz, rpy, axis, -0.2, 0.3))
+        else:
+            js.append(("revolute", xyz, rpy, axis, -2.5, 2.5))
+    return synth_urdf(js, tip)
+
+
+@pytest.mark.parametrize("n,pris,tip,tiles", [
+    (8, (), ("0 0.05 0.1", "0.3 0 0.2"), (1, 8, 16)),      # n == tile width: the tip cannot ride the scan (8 lanes)
+    (8, (), None, (1, 8)),                                   # no tip joint at all
+    (16, (), ("0 0 0.1", "0 0 0"), (16, 32)),                # n == 16
+    (5, (2,), ("0.1 0 0", "0 0.5 0"), (1, 8)),               # prismatic joint mid-chain (reference FK supports it)
+    (4, (0, 3), None, (1, 8, 32)),                           # prismatic first and last
+    (1, (), ("0 0 0.2", "0 0 0"), (1, 8)),                   # single joint
+    (12, (5,), ("0 0 0.1", "0.1 0 0"), (16, 32)),            # tile kernel only (n > 8), with a prismatic joint
+])
+def test_chain_shapes_match_twin_and_oracle(n, pris, tip, tiles):
+    urdf, base, ee = arm(n, pris, tip)
+    r = ob.Robot.from_urdf_str(urdf, base, ee)
+    ch = O.Chain(r.chain())
+    assert ch.n == n
+    rng = np.random.default_rng(100 + n)
+    # evaluator vs the golden-pinned oracle (FK + Jacobian incl. prismatic columns + objective + gradient)
+    q = rng.uniform(ch.lb, ch.ub, size=(33, n))
+    tg = targets_for(ch, rng, 33)
+    out = r.eval_batch(q, tg)
+    for i in range(0, 33, 4):
+        assert np.abs(out["ee"][i, :7] - ch.fk(q[i])[1][:7]).max() < 1e-12
+        assert np.abs(out["jac"][i].reshape(n, 6).T - ch.joint_jacobian(q[i])).max() < 1e-12
+        assert abs(out["f"][i] - ch.objective(q[i], tg[i])) <= 1e-12 * max(1.0, out["f"][i])
+        g = ch.objective_grad(q[i], tg[i])
+        assert np.abs(out["grad"][i] - g).max() <= 1e-11 * max(1.0, np.abs(g).max())
+    # solver vs twin per seed, every layout that fits
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    x0 = 0.5 * (ch.lb + ch.ub)
+    R = 256
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    for tile in tiles:
+        qq, f, st, ev = r.ik_attempts(cfg, tgt, x0, R, tile=tile)
+        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, 0, R, O.twin_params(layout=twin_layout(ch, tile)))
+        assert np.array_equal(st, tst) and np.array_equal(ev, tev), tile
+        assert np.array_equal(qq, tq), tile
+        ok = st == 1
+        if n > 1:
+            assert ok.sum() > 0
+        for i in np.where(ok)[0][:16]:
+            assert ch.objective(qq[i], tgt) < cfg.tol_f and np.all(qq[i] >= ch.lb) and np.all(qq[i] <= ch.ub)
+
+
+def test_edge_cases_empty_ragged_and_limits():
+    r, ch = robot_and_chain("ur5")
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=4)
+    # empty batch
+    q, f, st = r.ik_batch(cfg, np.zeros((0, 8)), np.zeros((0, 6)), restarts=4)
+    assert q.shape == (0, 6) and st.shape == (0,)
+    assert r.eval_batch(np.zeros((0, 6)))["ee"].shape == (0, 8)
+    # T = 1, R = 1 (restart 0 only = the caller's seed), seed exactly on a solution -> converges at evaluation 1
+    qs = np.array([0.3, -0.4, 0.5, 0.1, -0.2, 0.6])
+    tgt = ch.fk(qs)[1]
+    q, f, st, extra = r.ik_batch(cfg, tgt[None], qs[None], restarts=1, stats=True)
+    assert st[0] == 1 and extra["evals"][0] == 1 and np.array_equal(q[0], qs)
+    # seeds outside the limits are rejected on the host path (lib.rs:251-254)
+    bad = qs.copy()
+    bad[2] = ch.ub[2] + 1.0
+    with pytest.raises(ob.OptikError, match="joint limits"):
+        r.ik_batch(cfg, tgt[None], bad[None], restarts=4)
+    # seed exactly on the limits is legal
+    edge = ch.ub.copy()
+    q, f, st = r.ik_batch(cfg, tgt[None], edge[None], restarts=4)
+    assert st.shape == (1,)
+    # more chunks than restarts, odd sizes
+    T = 37
+    rng = np.random.default_rng(4)
+    tg = targets_for(ch, rng, T)
+    x0 = rng.uniform(ch.lb, ch.ub, size=(T, 6))
+    a = r.ik_batch(cfg, tg, x0, restarts=3, chunks=7)
+    b = r.ik_batch(cfg, tg, x0, restarts=3, chunks=1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+def test_infinite_limits_chain_solves():
+    """upper-lower <= 0 means unlimited (kinematics.rs:299-303); restart seeds then draw from [-pi, pi] (documented)."""
+    js = [("revolute", "0 0 0.1", "0 0 0", "0 0 1", 0, 0), ("revolute", "0.2 0 0", "1.2 0 0", "0 0 1", 0, 0),
+          ("revolute", "0.2 0 0", "0 0.7 0", "0 1 0", -2, 2), ("revolute", "0.1 0 0.1", "0 0 0.4", "1 0 0", 0, 0),
+          ("revolute", "0 0.1 0", "0.5 0 0", "0 0 1", -2, 2), ("revolute", "0 0 0.1", "0 0.9 0", "0 1 0", 0, 0)]
+    urdf, base, ee = synth_urdf(js, ("0 0 0.1", "0 0 0"))
+    r = ob.Robot.from_urdf_str(urdf, base, ee)
+    ch = O.Chain(r.chain())
+    assert np.isinf(ch.lb[0]) and np.isinf(ch.ub[0])
+    tgt = ch.fk(np.array([0.4, -0.3, 0.8, 0.2, -0.5, 0.1]))[1]
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=128)
+    q, f, st, ev = r.ik_attempts(cfg, tgt, np.zeros(6), 128)
+    tq, tf, tst, tev = O.twin_attempts(ch, tgt, np.zeros(6), 0, 128, O.twin_params(layout=1))
+    assert np.array_equal(st, tst) and np.array_equal(q, tq)
+    assert (st == 1).sum() > 10
+    for i in np.where(st == 1)[0][:8]:
+        assert ch.objective(q[i], tgt) < 1e-6
