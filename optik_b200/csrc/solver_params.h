@@ -31,8 +31,8 @@ enum {
 #define OPTIK_LM_LAMBDA_INC 10.0
 #define OPTIK_LM_LAMBDA_MIN 1e-9
 #define OPTIK_LM_LAMBDA_MAX 1e6
-#define OPTIK_LM_STALL_REL 1e-2
-#define OPTIK_LM_STALL_COUNT 3
+#define OPTIK_LM_STALL_REL 1e-1
+#define OPTIK_LM_STALL_COUNT 2
 
 struct SolveParams {
   // problem
