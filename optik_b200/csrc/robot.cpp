@@ -24,7 +24,8 @@
 #include "urdf.hpp"
 
 extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, void* stream);
-extern "C" int optik_launch_select(const SelectParams* p, void* stream);
+extern "C" int optik_launch_select(const SelectParams* p, unsigned slices, void* partial_scratch, void* stream);
+extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n);
@@ -328,6 +329,10 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const bool use_found = (cfg->solution_mode == OPTIK_MODE_SPEED) && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
   const size_t off_queue = carve(sizeof(unsigned long long));
+  // selection: slice the candidate range when one target has very many chunks
+  unsigned slices = 1;
+  if (C >= 4096) { slices = (unsigned)((C + 1023) / 1024); if (slices > 256) slices = 256; }
+  const size_t off_part = slices > 1 ? carve((size_t)T * slices * optik_select_partial_bytes()) : 0;
   char* scratch = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, s));
   P.cand_q = direct ? d_q : (double*)(scratch + off_q);
@@ -352,7 +357,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     S.cand_status = P.cand_status; S.cand_evals = P.cand_evals;
     S.tol_f = cfg->tol_f; S.tol_df_user = cfg->tol_df; S.tol_dx = cfg->tol_dx;
     S.record_out = d_best_record;
-    CUDA_TRY(optik_launch_select(&S, s));
+    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
   }
   if (!direct) {
     if (T > 0x7fffffffull) return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
@@ -364,7 +369,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     S.q_out = d_q; S.f_out = d_f; S.status_out = d_status;
     S.restart_out = (unsigned long long*)d_restart;  // optional
     S.evals_out = d_evals;                            // optional
-    CUDA_TRY(optik_launch_select(&S, s));
+    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
   }
   CUDA_TRY(cudaFreeAsync(scratch, s));
   return OPTIK_OK;

@@ -340,49 +340,69 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
 }
 
 // ------------------------------------------------------------------ selection across chunks (lib.rs:397-413)
-// One block per target: lexicographic min over the C candidates of (no-solution, score, restart index).
+// Lexicographic min over the C candidates of a target of (no-solution, score, restart index).  Grid = (T, S): each
+// block reduces one slice of the candidates; with S > 1 (one target, tens of thousands of chunks) the slice winners go
+// to a partial array and a second launch (P.final_pass) reduces the S partials -- a single block walking 65 536
+// records serially costs more than the solve itself.
+struct SelKey {
+  int has;  // 1 converged, 0 not, -1 nothing scanned
+  int evals;
+  double score;
+  unsigned long long restart;
+  unsigned long long idx;  // candidate index (job)
+};
+DEV bool sel_better(const SelKey& a, const SelKey& b) {  // a better than b
+  return (a.has > b.has) || (a.has == b.has && (a.score < b.score || (a.score == b.score && a.restart < b.restart)));
+}
 __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ SelectParams P) {
   const unsigned long long t = blockIdx.x;
-  __shared__ double s_score[256];
-  __shared__ unsigned long long s_restart[256];
-  __shared__ unsigned int s_idx[256];
-  __shared__ int s_has[256];
-  __shared__ int s_evals[256];
-  int has = 0, ev = 0;
-  double score = 0.0;
-  unsigned long long restart = ~0ull;
-  unsigned int idx = 0;
-  for (unsigned int c = threadIdx.x; c < P.C; c += blockDim.x) {
-    const unsigned long long job = t * P.C + c;
-    const int st = P.cand_status[job];
-    const int ok = (P.tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (P.tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
-                   (P.tol_dx >= 0.0 && st == OPTIK_ST_XTOL);
-    const double sc = P.cand_score[job];
-    const unsigned long long rr = P.cand_restart[job];
-    ev += P.cand_evals[job];
-    const bool better = (ok > has) || (ok == has && (sc < score || (sc == score && rr < restart)));
-    if (c == threadIdx.x || better) { has = ok; score = sc; restart = rr; idx = c; }
+  const unsigned S = gridDim.y, slice = blockIdx.y;
+  __shared__ SelKey s_key[256];
+  SelKey me;
+  me.has = -1; me.evals = 0; me.score = 0.0; me.restart = ~0ull; me.idx = t * P.C;
+  if (!P.final_pass) {
+    const unsigned long long per = ((unsigned long long)P.C + S - 1) / S;
+    const unsigned long long c0 = slice * per, c1 = (c0 + per < P.C) ? c0 + per : P.C;
+    for (unsigned long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+      const unsigned long long job = t * P.C + c;
+      const int st = P.cand_status[job];
+      SelKey k;
+      k.has = (P.tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (P.tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
+              (P.tol_dx >= 0.0 && st == OPTIK_ST_XTOL);
+      k.score = P.cand_score[job];
+      k.restart = P.cand_restart[job];
+      k.idx = job;
+      k.evals = 0;
+      me.evals += P.cand_evals[job];
+      if (me.has < 0 || sel_better(k, me)) { const int ev = me.evals; me = k; me.evals = ev; }
+    }
+  } else {  // reduce the S partial winners of target t
+    for (unsigned s = threadIdx.x; s < P.partials; s += blockDim.x) {
+      const SelKey k = P.partial[t * P.partials + s];
+      const int ev = me.evals + k.evals;
+      if (k.has >= 0 && (me.has < 0 || sel_better(k, me))) me = k;
+      me.evals = ev;
+    }
   }
-  if (threadIdx.x >= P.C) { has = -1; }  // no candidate scanned
-  s_has[threadIdx.x] = has; s_score[threadIdx.x] = score; s_restart[threadIdx.x] = restart; s_idx[threadIdx.x] = idx;
-  s_evals[threadIdx.x] = ev;
+  s_key[threadIdx.x] = me;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) {
-      const int o = threadIdx.x + s;
-      const bool better = (s_has[o] > s_has[threadIdx.x]) ||
-                          (s_has[o] == s_has[threadIdx.x] &&
-                           (s_score[o] < s_score[threadIdx.x] ||
-                            (s_score[o] == s_score[threadIdx.x] && s_restart[o] < s_restart[threadIdx.x])));
-      if (better) {
-        s_has[threadIdx.x] = s_has[o]; s_score[threadIdx.x] = s_score[o];
-        s_restart[threadIdx.x] = s_restart[o]; s_idx[threadIdx.x] = s_idx[o];
-      }
-      s_evals[threadIdx.x] += s_evals[o];
+      const SelKey o = s_key[threadIdx.x + s];
+      SelKey m = s_key[threadIdx.x];
+      const int ev = m.evals + o.evals;
+      if (o.has >= 0 && (m.has < 0 || sel_better(o, m))) m = o;
+      m.evals = ev;
+      s_key[threadIdx.x] = m;
     }
     __syncthreads();
   }
-  const unsigned long long win = t * P.C + s_idx[0];
+  const SelKey w = s_key[0];
+  if (!P.final_pass && S > 1) {  // slice winner -> partial array
+    if (threadIdx.x == 0) P.partial_out[t * S + slice] = w;
+    return;
+  }
+  const unsigned long long win = w.idx;
   if (P.q_out)
     for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[t * P.n + j] = P.cand_q[win * P.n + j];
   if (P.record_out) {
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     for (int j = threadIdx.x; j < P.n; j += blockDim.x) rec[8 + j] = P.cand_q[win * P.n + j];
     if (threadIdx.x == 0) {
       const unsigned long long rr = P.cand_restart[win];
-      rec[0] = s_has[0] > 0 ? 1.0 : 0.0;
+      rec[0] = w.has > 0 ? 1.0 : 0.0;
       rec[1] = (P.mode == 2) ? (double)rr : P.cand_score[win];
       rec[2] = (double)rr;
       rec[3] = P.cand_f[win];
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     P.f_out[t] = P.cand_f[win];
     if (P.restart_out) P.restart_out[t] = P.cand_restart[win];
     P.status_out[t] = P.cand_status[win];
-    if (P.evals_out) P.evals_out[t] = s_evals[0];
+    if (P.evals_out) P.evals_out[t] = w.evals;
   }
 }
 
@@ -447,8 +467,19 @@ extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, vo
   }
   return (int)cudaGetLastError();
 }
-extern "C" int optik_launch_select(const SelectParams* p, void* stream) {
-  optik::select_kernel<<<(unsigned)p->T, 256, 0, (cudaStream_t)stream>>>(*p);
+extern "C" int optik_select_partial_bytes(void) { return (int)sizeof(optik::SelKey); }
+// slices == 1: one launch.  slices > 1: caller provides partial scratch (T*slices*optik_select_partial_bytes()).
+extern "C" int optik_launch_select(const SelectParams* p, unsigned slices, void* partial_scratch, void* stream) {
+  SelectParams P = *p;
+  P.final_pass = 0; P.partials = 0; P.partial = nullptr; P.partial_out = nullptr;
+  if (slices <= 1) {
+    optik::select_kernel<<<dim3((unsigned)P.T, 1), 256, 0, (cudaStream_t)stream>>>(P);
+    return (int)cudaGetLastError();
+  }
+  P.partial_out = (optik::SelKey*)partial_scratch;
+  optik::select_kernel<<<dim3((unsigned)P.T, slices), 256, 0, (cudaStream_t)stream>>>(P);
+  P.final_pass = 1; P.partials = slices; P.partial = (const optik::SelKey*)partial_scratch; P.partial_out = nullptr;
+  optik::select_kernel<<<dim3((unsigned)P.T, 1), 256, 0, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm) {

@@ -71,6 +71,7 @@ struct SolveParams {
   unsigned long long* counters;       // [0] attempts run, [1] evaluations, [2] converged attempts (optional)
 };
 
+namespace optik { struct SelKey; }
 struct SelectParams {
   unsigned long long T;
   uint32_t C;
@@ -89,6 +90,11 @@ struct SelectParams {
   int* evals_out;                    // [T] total evaluations spent on the target
   double* record_out;                // [T][8+n] packed candidate record (see optik_b200.h), may be null
   int mode;                          // 1 Quality, 2 Speed (record score)
+  // two-level reduction for targets with very many chunks (set by optik_launch_select)
+  int final_pass;
+  unsigned partials;
+  const optik::SelKey* partial;
+  optik::SelKey* partial_out;
 };
 
 struct EvalParams {
