@@ -159,3 +159,15 @@ def test_product_never_touches_the_oracle():
                 assert "liboptik_oracle" not in text and '#include "../../oracle' not in text, f
     out = subprocess.run(["ldd", ob.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_header_is_valid_c_and_links(tmp_path):
+    exe = tmp_path / "c_abi_probe"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_probe.c"), "-o", str(exe),
+                           ob.LIB_PATH, "-Wl,-rpath," + os.path.dirname(ob.LIB_PATH)])
+    base, ee = ob.ROBOT_LINKS["panda"]
+    p = subprocess.run([str(exe), ob.data_path("panda"), base, ee], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "n=7 joints=8 inside=1 lb0=-2.8973 ub0=2.8973" in p.stdout
+    assert "EE link 'nope' does not exist" in p.stdout
