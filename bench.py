@@ -159,6 +159,7 @@ def run_product(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     K, W, R = args.steps, max(args.warmup, 3), SEEDS_PER_GPU
     robot, lb, ub, qstar = make_targets(K + W)
