@@ -138,7 +138,7 @@ typedef struct optik_gpu_batch_opts {
   uint32_t blocks;         /* grid size; 0 = auto (multiple of the SM count) */
   int32_t memory;          /* 0: all data pointers are host memory; 1: device memory (async on `stream`) */
   const double* ee_offset; /* pose8 (host memory) or NULL = identity (lib.rs:245) */
-  uint64_t* restart_out;   /* [T] winning restart index, optional */
+  uint64_t* restart_out;   /* [T] winning restart index, optional (ignored by optik_gpu_ik_attempts: see best_record_out[2]) */
   int32_t* evals_out;      /* [T] objective evaluations spent on the target, optional */
   uint64_t* counters;      /* [3] += {attempts run, evaluations, converged attempts}, optional */
   /* optik_gpu_ik_attempts only: also run the selection pass (lib.rs:397-413) over the records and write ONE

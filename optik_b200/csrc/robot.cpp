@@ -313,6 +313,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   if (C > 0xffffffffull) return fail(OPTIK_ERR_INVALID, "too many chunks");
   P.C = (uint32_t)C;
   const unsigned long long njobs = T * C;
+  if (C > 1 && !per_attempt_records && T > 0x7fffffffull)
+    return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
   Plan plan = make_plan(r, tile, o ? o->blocks : 0, njobs);
   const int n = r->n;
   const bool direct = (C == 1) || per_attempt_records;  // candidate records ARE the outputs
@@ -360,7 +362,6 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
   }
   if (!direct) {
-    if (T > 0x7fffffffull) return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
     SelectParams S{};
     S.T = T; S.C = P.C; S.n = n; S.mode = cfg->solution_mode;
     S.cand_q = P.cand_q; S.cand_f = P.cand_f; S.cand_score = P.cand_score; S.cand_restart = P.cand_restart;

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     // ---------------- evaluate the trial point: backward recursion in the target's frame
     double2* trow = row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
     se3 B = load_pose8(s_tip);
+#pragma unroll 1
     for (int j = n - 1; j >= 0; j--) {
       const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
       const double2 c1 = jc[1], c4 = jc[4], c5 = jc[5];
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
       fc = ft; have_cur = 1;
 #pragma unroll
       for (int i = 0; i < 6; i++) rc[i] = rt[i];
+#pragma unroll 1
       for (int j = 0; j < n; j++) {
         const double2 a0 = trow[3 * j + 0], a1 = trow[3 * j + 1], a2 = trow[3 * j + 2];
         v3 top, bot;
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
 #pragma unroll
     for (int e = 0; e < 21; e++) Ap[e] = 0.0;
     unsigned free_mask = 0;
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
       const double2 a0 = crow[3 * j + 0], a1 = crow[3 * j + 1], a2 = crow[3 * j + 2];
       const double c[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     for (int a = 0; a < 6; a++) Ap[a * (a + 1) / 2 + a] = Ap[a * (a + 1) / 2 + a] + lambda;
     double y[6];
     ldl6_solve(Ap, rc, y);
+#pragma unroll 1
     for (int j = 0; j < n; j++) {
       const double2 a0 = crow[3 * j + 0], a1 = crow[3 * j + 1], a2 = crow[3 * j + 2];
       const double m = ((free_mask >> j) & 1u) ? 1.0 : 0.0;

@@ -35,10 +35,9 @@ tg, x0, lb, ub = targets(r, 2000, 1)
 tgh, x0h = tg.cpu().numpy(), x0.cpu().numpy()
 cfg = ob.SolverConfig()  # Speed, max_time 0.1, tol_f 1e-6
 lib = ob.load_library()
-from oracle import oracle as O  # only to convert pose8 -> 4x4 for the C call (test-side helper)
-mats = [np.ascontiguousarray(O.pose8_to_matrix(p).T).ravel() for p in tgh]
+mats = [np.ascontiguousarray(np.array(ob._rows_from_pose8(p)).T).ravel() for p in tgh]  # column-major 4x4
 cc = cfg._c()
-r.ik(cfg, O.pose8_to_matrix(tgh[0]), x0h[0])  # warm-up
+r.ik(cfg, ob._rows_from_pose8(tgh[0]), x0h[0])  # warm-up
 t0 = time.perf_counter(); ok1 = 0
 for i in range(2000):
     p = lib.optik_robot_ik(r._h, C.byref(cc), mats[i].ctypes.data_as(C.POINTER(C.c_double)), x0h[i].ctypes.data_as(C.POINTER(C.c_double)))
