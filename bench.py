@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.sm_max, self.error = [], set(), None, None
@@ -325,7 +325,7 @@ def run_product(args):
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step_median": float(np.median(e2e_times) * 1e3), "api": "Robot.ik_attempts(host numpy buffers, pinned) -> optik_gpu_ik_attempts (C ABI)"},
-            "gpu_launches": (2 if world == 1 else 3) * K,
+            "gpu_launches": (3 if world == 1 else 4) * K,  # per step: solve_t1 + select (slice pass + final pass) [+ select_records]
             "roofline": roof,
             "roofline_solve": {"kernel": "solve_t1_kernel" if (tile or 1) == 1 else f"solve_kernel<{tile}>", "bound": "fp64 issue / latency (not HBM)",
                                "hbm_gbs": attempts * solve_bytes / (dev_ms * 1e-3) / 1e9,

@@ -25,7 +25,7 @@ enum {
 // The blob is n joints followed by the fixed tip pose8 {qx,qy,qz,qw,tx,ty,tz,0}.
 
 // Levenberg-Marquardt constants of the in-warp solver (tuned on Panda/UR5/UR3e/snake).
-#define OPTIK_LM_MAX_EVALS 64
+#define OPTIK_LM_MAX_EVALS 32
 #define OPTIK_LM_LAMBDA0 1e-1
 #define OPTIK_LM_LAMBDA_DEC 0.3
 #define OPTIK_LM_LAMBDA_INC 10.0

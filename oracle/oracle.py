@@ -152,7 +152,7 @@ class TwinParams(C.Structure):
 
 
 # defaults of the kernel's LM iteration (DESIGN.md "Solver"); keep in sync with optik_b200/csrc/solver_params.h
-LM_DEFAULTS = dict(max_evals=64, lambda0=1e-1, lambda_dec=0.3, lambda_inc=10.0, lambda_min=1e-9, lambda_max=1e6,
+LM_DEFAULTS = dict(max_evals=32, lambda0=1e-1, lambda_dec=0.3, lambda_inc=10.0, lambda_min=1e-9, lambda_max=1e6,
                    stall_rel=1e-1, stall_count=2, layout=0)
 
 

@@ -87,7 +87,7 @@ def test_twin_solutions_pass_reference_predicate():
         for i in np.where(ok)[0]:
             assert ch.objective(q[i], tgt) < 1e-6
             assert np.all(q[i] >= ch.lb) and np.all(q[i] <= ch.ub)
-        assert np.all(ev <= 64)
+        assert np.all(ev <= 32)
 
 
 def test_unreachable_target_fails():  # tests/test_ik.rs:24-43 (impossible goal) -> no solution
