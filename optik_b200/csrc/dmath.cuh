@@ -63,7 +63,11 @@ DEV double dot6(const double* a, const double* b) {
 
 // sin/cos: Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4].
 DEV void dsincos(double x, double& sn, double& cs) {
-  const double k = rint(x * 6.36619772367581382433e-01);
+  // k = rint(x * 2/pi) by the 1.5*2^52 shift (two fp64 adds instead of a round + a 64-bit convert, which run at a
+  // quarter of the fp64 rate); the quadrant is the low two bits of the shifted value's mantissa.  Same result as
+  // rint for |x * 2/pi| < 2^51; the CPU twin uses the identical sequence.
+  const double kk = x * 6.36619772367581382433e-01 + 6755399441055744.0;
+  const double k = kk - 6755399441055744.0;
   double r = fma(-k, 1.57079632673412561417e+00, x);
   r = fma(-k, 6.07710050630396597660e-11, r);
   r = fma(-k, 2.02226624871116645580e-21, r);
@@ -80,7 +84,7 @@ DEV void dsincos(double x, double& sn, double& cs) {
   pc = fma(z, pc, -1.38888888888741095749e-03);
   pc = fma(z, pc, 4.16666666666666019037e-02);
   const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const int q = (int)((long long)k & 3);
+  const int q = __double2loint(kk) & 3;
   double ss = (q & 1) ? c : s;
   double cc = (q & 1) ? s : c;
   if (q == 1 || q == 2) cc = -cc;

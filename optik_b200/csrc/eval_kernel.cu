@@ -9,15 +9,16 @@
 // This is the HBM-bound kernel of the design: per configuration it reads q (8n B) + target (64 B) and writes the
 // pose (64 B), the 6 x n Jacobian (48n B), f (8 B) and the gradient (8n B) = 8(8n+17) bytes in fp64.
 //
-// Algorithm: a single BACKWARD recursion  B_{j-1} = L_j * B_j  (B_n = tip, L_j = origin_j * motion_j(q_j)) carries
-// the pose of the end effector in joint j's frame; the body-frame Jacobian column of joint j is then
-//   [ R_Bj^T (axis_j x p_Bj) ; R_Bj^T axis_j ]
-// and B_0 is the end-effector pose -- no per-joint transforms are stored, so the register footprint is
-// independent of n.  Every thread stages its 6n-double Jacobian row in shared memory with 128-bit stores (row stride
-// = an odd number of 16-byte units, so quarter-warps never bank-conflict), forms the gradient from it, and then hands
-// the row to the TMA: one `cp.async.bulk.global.shared::cta` per thread writes the 48n contiguous bytes to HBM while
-// the thread already works on its next configuration (it only waits for the bulk read of its own row before
-// overwriting it).  No block barrier in the loop.  The chain is staged once per block with a 1-D TMA bulk load.
+// Algorithm: a single BACKWARD recursion over the joints carries C_j = B_j^-1, the inverse of the end-effector pose in
+// joint j's frame (B_{j-1} = L_j B_j, B_n = tip, L_j = origin_j * motion_j(q_j)); the body-frame Jacobian column of
+// joint j is [ t_C x (R_C axis_j) ; R_C axis_j ] = [ R_Bj^T (axis_j x p_Bj) ; R_Bj^T axis_j ]  (kinematics.rs:171-193)
+// and C_0^-1 is the end-effector pose -- no per-joint transforms are stored, so the register footprint is independent
+// of n.  Inputs: each warp streams its tiles of 32 joint vectors into shared memory with one TMA bulk load per tile,
+// issued one tile ahead; targets are loaded into registers before the recursion that hides their latency.  Outputs:
+// every thread stages its 6n-double Jacobian row in shared memory with 128-bit stores (row stride = an odd number of
+// 16-byte units, so quarter-warps never bank-conflict), forms the gradient from it, and hands the row to the TMA: one
+// `cp.async.bulk.global.shared::cta` per thread writes the 48n contiguous bytes to HBM while the thread already works
+// on its next configuration.  No block barrier in the loop.  The chain is staged once per block with a TMA bulk load.
 #include <cuda_runtime.h>
 
 #include "dmath.cuh"
@@ -28,6 +29,7 @@ namespace optik {
 DEV uint32_t e_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 constexpr int EVAL_THREADS = 128;
+constexpr int EVAL_WARPS = EVAL_THREADS / 32;
 
 DEV se3 e_load_pose8(const double* p) {
   se3 r;
@@ -43,83 +45,155 @@ DEV v3 e_weight3(qt tq, const double* w, v3 u) {
 
 DEV int eval_row_units(int n) { return (3 * n) | 1; }  // 16-byte units per staged row, forced odd
 
-__global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(const __grid_constant__ EvalParams P) {
-  extern __shared__ __align__(128) double smem[];
-  // layout: chain blob | mbarrier (16 B) | per-thread Jacobian rows
-  double* s_chain = smem;
-  const int n = P.n;
-  const int chain_doubles = OPTIK_CHAIN_STRIDE * n + 8;
-  uint64_t* s_bar = (uint64_t*)(smem + chain_doubles);
-  double2* s_rows = (double2*)(smem + chain_doubles + 2);
-  const int units = eval_row_units(n);
-
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e_smem_u32(s_bar)), "r"(P.chain_bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     e_smem_u32(s_chain)),
-                 "l"(P.chain), "r"(P.chain_bytes), "r"(e_smem_u32(s_bar))
-                 : "memory");
-  }
+DEV void e_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
-        : "r"(e_smem_u32(s_bar)), "r"(0u)
+        : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// one 1-D TMA bulk load global -> shared, completion counted on `bar`
+DEV void e_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
+// N = compile-time joint count (fully unrolled joint loops: static shared-memory offsets, the scheduler overlaps one
+// joint's sin/cos with the previous joint's quaternion chain); N = 0 reads n from the parameters.
+template <int N>
+__global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_constant__ EvalParams P) {
+  extern __shared__ __align__(128) double smem[];
+  // layout: chain blob | block mbarrier (16 B) | one mbarrier per warp (8 B each) | per-thread Jacobian rows |
+  //         per-warp joint-vector tiles [EVAL_WARPS][32 * n] | per-joint constants origin_q (x) axis [n][4]
+  double* s_chain = smem;
+  const int n = N ? N : P.n;
+  const int chain_doubles = OPTIK_CHAIN_STRIDE * n + 8;
+  uint64_t* s_bar = (uint64_t*)(smem + chain_doubles);
+  uint64_t* s_wbar = (uint64_t*)(smem + chain_doubles + 2);
+  double2* s_rows = (double2*)(smem + chain_doubles + 2 + EVAL_WARPS);
+  const int units = eval_row_units(n);
+  double* s_q = (double*)(s_rows + (size_t)EVAL_THREADS * units);
+  double2* s_oa = (double2*)(s_q + (size_t)EVAL_WARPS * 32 * n);  // [n][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_bar)));
+#pragma unroll
+    for (int w = 0; w < EVAL_WARPS; w++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_wbar + w)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) e_bulk_load(e_smem_u32(s_chain), P.chain, P.chain_bytes, e_smem_u32(s_bar));
+
+  // ---- input pipeline: every warp streams ITS tiles of 32 joint vectors (32 * n contiguous doubles of q) into
+  // shared memory with one TMA bulk load per tile; the load of tile k+1 is issued as soon as the recursion of tile k
+  // has consumed the buffer and lands while the warp forms objective / gradient / stores of tile k.  No thread ever
+  // waits on a dependent global load of q inside the joint loop.  Ragged last tile / unaligned q: plain loads.
+  double* qb = s_q + (size_t)warp * 32 * n;
+  const uint32_t qb_addr = e_smem_u32(qb), wbar = e_smem_u32(s_wbar + warp);
+  const uint32_t tile_bytes = 256u * (uint32_t)n;
+  const bool q_aligned = (((unsigned long long)P.q) & 15ull) == 0ull;
+  const unsigned long long stride = (unsigned long long)gridDim.x * EVAL_THREADS;
+  unsigned long long base = (unsigned long long)blockIdx.x * EVAL_THREADS + 32ull * warp;  // first configuration of my tile
+  uint32_t parity = 0;
+  bool pending = false;
+  auto fetch_tile = [&](unsigned long long b) {
+    if (q_aligned && b + 32 <= P.B) {
+      if (lane == 0) e_bulk_load(qb_addr, P.q + b * n, tile_bytes, wbar);
+      return true;
+    }
+    if (b + lane < P.B)
+      for (int j = 0; j < n; j++) qb[lane * n + j] = P.q[(b + lane) * n + j];
+    return false;
+  };
+  if (base < P.B) pending = fetch_tile(base);
+  e_mbar_wait(e_smem_u32(s_bar), 0);  // chain staged
+
+  if (threadIdx.x < n) {  // per-joint constant origin_q (x) (axis, 0)
+    const double* jc = s_chain + OPTIK_CHAIN_STRIDE * threadIdx.x;
+    qt oq, qa;
+    oq.x = jc[4]; oq.y = jc[5]; oq.z = jc[6]; oq.w = jc[7];
+    qa.x = jc[8]; qa.y = jc[9]; qa.z = jc[10]; qa.w = 0.0;
+    const qt oa = qmul(oq, qa);
+    s_oa[2 * threadIdx.x] = make_double2(oa.x, oa.y);
+    s_oa[2 * threadIdx.x + 1] = make_double2(oa.z, oa.w);
+  }
+  __syncthreads();
   const se3 tip = se3mul(e_load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), e_load_pose8(P.ee_offset));
+  se3 tip_inv;
+  tip_inv.q = qconj(tip.q);
+  tip_inv.t = neg3(qrot(tip_inv.q, tip.t));
   const bool want_obj = (P.f_out != nullptr) || (P.grad_out != nullptr);
   const bool want_cols = (P.jac_out != nullptr) || (P.grad_out != nullptr);
   double2* my = s_rows + (size_t)threadIdx.x * units;
   const uint32_t my_addr = e_smem_u32(my);
   const uint32_t row_bytes = 48u * (uint32_t)n;
+  const double* q = qb + lane * n;
 
-  for (unsigned long long i = (unsigned long long)blockIdx.x * EVAL_THREADS + threadIdx.x; i < P.B;
-       i += (unsigned long long)gridDim.x * EVAL_THREADS) {
+  for (; base < P.B; base += stride) {
+    const unsigned long long i = base + lane;
+    const bool active = i < P.B;
     // my previous row must have been read out by the TMA before it is overwritten
     if (P.jac_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    se3 B = tip;
-    const double* q = P.q + i * n;
-    for (int j = n - 1; j >= 0; j--) {
-      const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
-      const double2 c0 = jc[0], c1 = jc[1], c2 = jc[2], c3 = jc[3], c4 = jc[4], c5 = jc[5];
-      const v3 ot = mk3(c0.x, c0.y, c1.x);
-      const int type = (int)c1.y;
-      qt oq;
-      oq.x = c2.x; oq.y = c2.y; oq.z = c3.x; oq.w = c3.y;
-      const v3 ax = mk3(c4.x, c4.y, c5.x);
-      if (want_cols) {  // column of joint j from B_j (pose of the EE in frame j)
-        const v3 lin = qrot_inv(B.q, (type == 0) ? cross3(ax, B.t) : ax);
-        v3 ang = qrot_inv(B.q, ax);
-        if (type != 0) ang = mk3(0, 0, 0);
-        my[3 * j + 0] = make_double2(lin.x, lin.y);
-        my[3 * j + 1] = make_double2(lin.z, ang.x);
-        my[3 * j + 2] = make_double2(ang.y, ang.z);
-      }
-      // B_{j-1} = origin_j * motion_j(q_j) * B_j
-      se3 L;
-      const double qj = q[j];
-      if (type == 0) {
-        double s, c;
-        dsincos(0.5 * qj, s, c);
-        qt qa;
-        qa.x = ax.x * s; qa.y = ax.y * s; qa.z = ax.z * s; qa.w = c;
-        L.q = qmul(oq, qa);
-        L.t = ot;
-      } else {
-        L.q = oq;
-        L.t = add3(ot, qrot(oq, scale3(ax, qj)));
-      }
-      B = se3mul(L, B);
+    // the target is not needed before the recursion ends: its loads fly underneath it
+    double2 t0 = make_double2(0, 0), t1 = make_double2(0, 1), t2 = make_double2(0, 0), t3 = make_double2(0, 0);
+    if (want_obj && active) {
+      const double2* tp = (const double2*)(P.targets + (unsigned long long)P.target_stride * i);
+      t0 = tp[0]; t1 = tp[1]; t2 = tp[2]; t3 = tp[3];
     }
+    if (pending) { e_mbar_wait(wbar, parity); parity ^= 1u; }
+    // Backward recursion on the INVERSE pose C_j = B_j^-1 = (R_B^T, -R_B^T p_B): the column of joint j is then
+    //   ang = R_C axis_j ,  lin = t_C x ang      [ = R_B^T (axis_j x p_B) ]
+    // (one rotation + one cross product instead of two rotations), and  C_{j-1} = C_j L_j^-1  with
+    //   L_j.q = cos * origin_q + sin * (origin_q (x) axis)   (the second factor is a per-joint constant, s_oa)
+    //   C.q <- C.q (x) conj(L.q) ,  C.t <- C.t - R_C.q(new) origin_t
+    se3 Cinv = tip_inv;
+    if (active) {
+#pragma unroll
+      for (int j = n - 1; j >= 0; j--) {
+        const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
+        const double2 c0 = jc[0], c1 = jc[1], c2 = jc[2], c3 = jc[3], c4 = jc[4], c5 = jc[5];
+        v3 ot = mk3(c0.x, c0.y, c1.x);
+        const int type = (int)c1.y;
+        const v3 ax = mk3(c4.x, c4.y, c5.x);
+        if (want_cols) {
+          v3 ang = qrot(Cinv.q, ax), lin;
+          if (type == 0) lin = cross3(Cinv.t, ang);
+          else { lin = ang; ang = mk3(0, 0, 0); }
+          my[3 * j + 0] = make_double2(lin.x, lin.y);
+          my[3 * j + 1] = make_double2(lin.z, ang.x);
+          my[3 * j + 2] = make_double2(ang.y, ang.z);
+        }
+        const double qj = q[j];
+        qt lq;  // conj(L.q)
+        if (type == 0) {
+          double s, c;
+          dsincos(0.5 * qj, s, c);
+          const double2 a0 = s_oa[2 * j], a1 = s_oa[2 * j + 1];
+          lq.x = -fma(c, c2.x, s * a0.x); lq.y = -fma(c, c2.y, s * a0.y); lq.z = -fma(c, c3.x, s * a1.x);
+          lq.w = fma(c, c3.y, s * a1.y);
+        } else {
+          lq.x = -c2.x; lq.y = -c2.y; lq.z = -c3.x; lq.w = c3.y;
+          qt oq;
+          oq.x = c2.x; oq.y = c2.y; oq.z = c3.x; oq.w = c3.y;
+          ot = add3(ot, qrot(oq, scale3(ax, qj)));
+        }
+        Cinv.q = qmul(Cinv.q, lq);
+        Cinv.t = sub3(Cinv.t, qrot(Cinv.q, ot));
+      }
+    }
+    se3 B;  // end-effector pose = C_0^-1
+    B.q = qconj(Cinv.q);
+    B.t = neg3(qrot(B.q, Cinv.t));
+    // the tile buffer is free once every lane has finished its recursion: stream the warp's next tile into it
+    __syncwarp();
+    pending = (base + stride < P.B) ? fetch_tile(base + stride) : false;
+    if (!active) continue;
     if (P.jac_out) {  // hand the staged row to the TMA: 48n contiguous bytes of HBM per configuration
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.jac_out + i * 6ull * n),
@@ -133,7 +207,9 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(const __grid_constan
       o[2] = make_double2(B.t.x, B.t.y); o[3] = make_double2(B.t.z, 0.0);
     }
     if (want_obj) {
-      const se3 tgt = e_load_pose8(P.targets + (unsigned long long)P.target_stride * i);
+      se3 tgt;
+      tgt.q.x = t0.x; tgt.q.y = t0.y; tgt.q.z = t1.x; tgt.q.w = t1.y;
+      tgt.t = mk3(t2.x, t2.y, t3.x);
       const qt xq = qmul(qconj(tgt.q), B.q);
       const v3 xt = qrot_inv(tgt.q, sub3(B.t, tgt.t));
       double qw = xq.w;
@@ -183,6 +259,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(const __grid_constan
         const v3 wxs = cross3(w, s);
         const v3 ua = axpy3(ce, cross3(w, wxs), axpy3(-0.5, wxs, s));
         double* g = P.grad_out + i * n;
+#pragma unroll
         for (int j = 0; j < n; j++) {  // reading my own row while the TMA reads it too is fine
           const double2 a0 = my[3 * j + 0], a1 = my[3 * j + 1], a2 = my[3 * j + 2];
           const double gj = fma(ul.x, a0.x, fma(ul.y, a0.y, fma(ul.z, a1.x, fma(ua.x, a1.y, fma(ua.y, a2.x, ua.z * a2.y)))));
@@ -198,13 +275,33 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(const __grid_constan
 }  // namespace optik
 
 extern "C" int optik_eval_smem_bytes(int n);
+static const void* eval_entry(int n) {
+  switch (n) {
+    case 6: return (const void*)optik::eval_kernel<6>;
+    case 7: return (const void*)optik::eval_kernel<7>;
+    default: return (const void*)optik::eval_kernel<0>;
+  }
+}
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream) {
   const size_t smem = (size_t)optik_eval_smem_bytes(p->n);
-  cudaError_t e = cudaFuncSetAttribute(optik::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const void* fn = eval_entry(p->n);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  optik::eval_kernel<<<blocks, optik::EVAL_THREADS, smem, (cudaStream_t)stream>>>(*p);
-  return (int)cudaGetLastError();
+  void* args[] = {(void*)p};
+  e = cudaLaunchKernel(fn, dim3(blocks), dim3(optik::EVAL_THREADS), args, smem, (cudaStream_t)stream);
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 extern "C" int optik_eval_smem_bytes(int n) {
-  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2) + 16ull * optik::EVAL_THREADS * (size_t)((3 * n) | 1));
+  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2 + optik::EVAL_WARPS) +
+               16ull * optik::EVAL_THREADS * (size_t)((3 * n) | 1) + sizeof(double) * 32ull * n * optik::EVAL_WARPS +
+               sizeof(double) * 4ull * n);
+}
+// resident blocks per SM: the kernel is persistent (grid-stride over tiles), so the launcher sizes the grid to
+// exactly sm_count * this
+extern "C" int optik_eval_occupancy(int n, int* blocks_per_sm) {
+  const int smem = optik_eval_smem_bytes(n);
+  const void* fn = eval_entry(n);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, optik::EVAL_THREADS, smem);
 }

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <atomic>
 #include <mutex>
 #include <random>
 #include <sstream>
@@ -29,6 +30,7 @@ extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n);
+extern "C" int optik_eval_occupancy(int n, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
 extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm);
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
@@ -530,8 +532,16 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
   }
   if (ee_offset) for (int i = 0; i < 8; i++) P.ee_offset[i] = ee_offset[i];
   else pose8_identity(P.ee_offset);
-  const uint64_t nblk = (B + 127) / 128;
-  const int blocks = (int)(nblk < (uint64_t)robot->sm_count * 8 ? nblk : (uint64_t)robot->sm_count * 8);
+  // persistent grid: one wave of resident blocks, each striding over tiles of 128 configurations
+  static std::atomic<int> occ_cache[OPTIK_MAX_DOF + 1];  // blocks/SM per n (all GPUs of a box are alike)
+  int per_sm = occ_cache[n].load(std::memory_order_relaxed);
+  if (per_sm == 0) {
+    CUDA_TRY(optik_eval_occupancy(n, &per_sm));
+    occ_cache[n].store(per_sm, std::memory_order_relaxed);
+  }
+  if (per_sm < 1) return fail(OPTIK_ERR_UNSUPPORTED, "evaluator tile does not fit one SM");
+  const uint64_t nblk = (B + 127) / 128, resident = (uint64_t)robot->sm_count * (uint64_t)per_sm;
+  const int blocks = (int)(nblk < resident ? nblk : resident);
   if (memory == 1) {
     P.q = q; P.targets = targets; P.ee_out = ee_out; P.jac_out = jac_out; P.f_out = f_out; P.grad_out = grad_out;
     CUDA_TRY(optik_launch_eval(&P, blocks, s));

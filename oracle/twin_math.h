@@ -17,6 +17,7 @@
 #define TWIN_MATH_H
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 typedef struct { double x, y, z; } v3;
 typedef struct { double x, y, z, w; } qt;
@@ -66,7 +67,10 @@ static inline void tw_sincos(double x, double* sn, double* cs) {
   const double PIO2_1 = 1.57079632673412561417e+00;  /* first 33 bits of pi/2 */
   const double PIO2_2 = 6.07710050630396597660e-11;  /* next 33 bits */
   const double PIO2_3 = 2.02226624871116645580e-21;  /* remainder */
-  double k = rint(x * TWO_OVER_PI);
+  /* rint by the 1.5*2^52 shift, exactly as the kernels do it (csrc/dmath.cuh) */
+  const double SHIFT = 6755399441055744.0;
+  double kk = x * TWO_OVER_PI + SHIFT;
+  double k = kk - SHIFT;
   double r = fma(-k, PIO2_1, x);
   r = fma(-k, PIO2_2, r);
   r = fma(-k, PIO2_3, r);
@@ -85,7 +89,9 @@ static inline void tw_sincos(double x, double* sn, double* cs) {
   pc = fma(z, pc, -1.38888888888741095749e-03);
   pc = fma(z, pc, 4.16666666666666019037e-02);
   double c = fma(z * z, pc, fma(z, -0.5, 1.0));
-  int q = (int)((long long)k & 3);
+  uint64_t kbits;
+  memcpy(&kbits, &kk, sizeof kbits);
+  int q = (int)(kbits & 3u);
   double ss = (q & 1) ? c : s;
   double cc = (q & 1) ? s : c;
   if (q == 1 || q == 2) cc = -cc;
