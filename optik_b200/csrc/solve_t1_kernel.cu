@@ -2,8 +2,9 @@
 //
 // Same path, objective, stop rules, seeds and LM step as solve_kernel.cu (reference: crates/optik/src/lib.rs:297-413,
 // objective.rs:40-110, kinematics.rs:123-196, math.rs:40-203), but the evaluation order is sequential per seed:
-//   * one BACKWARD recursion  B_{j-1} = L_j B_j  (B_n = tip) in the target's frame yields the pose error X = B_0
-//     and, on the way, joint j's body-Jacobian column from B_j: [R_Bj^T (a_j x p_Bj); R_Bj^T a_j]  (as eval_kernel)
+//   * one BACKWARD recursion in the target's frame on the inverse pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip)
+//     yields joint j's body-Jacobian column [t_C x (R_C a_j); R_C a_j] = [R_Bj^T (a_j x p_Bj); R_Bj^T a_j] with one
+//     rotation and one cross product, and the pose error X = C_0^-1  (as eval_kernel)
 //   * columns live in a per-thread shared-memory row (128-bit accesses, odd 16-byte row stride => conflict-free);
 //     two rows per thread: the current point's task columns and the trial point's body columns (swapped on accept)
 //   * the 6x6 Gram matrix is accumulated joint by joint with fma; the LDL^T solve is thread-private.
@@ -47,7 +48,8 @@ DEV void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
 __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) double smem[];
   const int n = P.n;
-  // layout: chain blob | tip pose8 | mbarrier (16 B) | rows[2][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] | qnext[n][T]
+  // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[2][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
+  //         qnext[n][T] | per-joint constants origin_q (x) (axis, 0) [n][4]
   double* s_chain = smem;
   double* s_tip = smem + OPTIK_CHAIN_STRIDE * n + 8;
   uint64_t* s_bar = (uint64_t*)(s_tip + 8);
@@ -56,11 +58,23 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
   double* s_qc = (double*)(s_rows + 2 * T1_THREADS * units);
   double* s_qt = s_qc + n * T1_THREADS;
   double* s_qn = s_qt + n * T1_THREADS;
+  double* s_oa = s_qn + n * T1_THREADS;
   stage_chain_tma(s_chain, s_bar, P.chain, P.chain_bytes);
-  if (threadIdx.x == 0) {  // tip = fixed tip joint * ee_offset, once per block
+  if (threadIdx.x == 0) {  // (fixed tip joint * ee_offset)^-1, once per block
     const se3 tip = se3mul(load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), load_pose8(P.ee_offset));
-    s_tip[0] = tip.q.x; s_tip[1] = tip.q.y; s_tip[2] = tip.q.z; s_tip[3] = tip.q.w;
-    s_tip[4] = tip.t.x; s_tip[5] = tip.t.y; s_tip[6] = tip.t.z; s_tip[7] = 0.0;
+    const qt iq = qconj(tip.q);
+    const v3 it = neg3(qrot(iq, tip.t));
+    s_tip[0] = iq.x; s_tip[1] = iq.y; s_tip[2] = iq.z; s_tip[3] = iq.w;
+    s_tip[4] = it.x; s_tip[5] = it.y; s_tip[6] = it.z; s_tip[7] = 0.0;
+  }
+  if (threadIdx.x < n) {  // origin_q (x) (axis, 0): L_j.q = cos * origin_q + sin * this
+    const double* jc = s_chain + OPTIK_CHAIN_STRIDE * threadIdx.x;
+    qt oq, qa;
+    oq.x = jc[4]; oq.y = jc[5]; oq.z = jc[6]; oq.w = jc[7];
+    qa.x = jc[8]; qa.y = jc[9]; qa.z = jc[10]; qa.w = 0.0;
+    const qt oa = qmul(oq, qa);
+    double* d = s_oa + 4 * threadIdx.x;
+    d[0] = oa.x; d[1] = oa.y; d[2] = oa.z; d[3] = oa.w;
   }
   __syncthreads();
 
@@ -81,6 +95,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
   bool running = false, job_open = false, best_has = false, rec_any = false, have_next = false, queue_done = false, done = false;
   se3 O0;  // origin of joint 0 pre-multiplied by T_tgt^-1 (FK in the target's frame)
   O0.q.x = O0.q.y = O0.q.z = 0; O0.q.w = 1; O0.t = mk3(0, 0, 0);
+  qt O0a = O0.q;  // O0.q (x) (axis_0, 0)
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
@@ -146,6 +161,9 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
           o0.q.x = s_chain[4]; o0.q.y = s_chain[5]; o0.q.z = s_chain[6]; o0.q.w = s_chain[7];
           o0.t = mk3(s_chain[0], s_chain[1], s_chain[2]);
           O0 = se3mul(ti, o0);
+          qt a0;
+          a0.x = s_chain[8]; a0.y = s_chain[9]; a0.z = s_chain[10]; a0.w = 0.0;
+          O0a = qmul(O0.q, a0);
           best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
           for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[tgt_id * n + j];  // record if no attempt runs
           P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = nxt_r;
@@ -174,40 +192,47 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
 
     // ---------------- evaluate the trial point: backward recursion in the target's frame
     double2* trow = row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
-    se3 B = load_pose8(s_tip);
+    se3 Ci = load_pose8(s_tip);  // C_n = tip^-1
 #pragma unroll 1
     for (int j = n - 1; j >= 0; j--) {
       const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
       const double2 c1 = jc[1], c4 = jc[4], c5 = jc[5];
       const int type = (int)c1.y;
       const v3 ax = mk3(c4.x, c4.y, c5.x);
-      v3 lin, ang = qrot_inv(B.q, ax);
-      if (type == 0) lin = qrot_inv(B.q, cross3(ax, B.t));
+      v3 lin, ang = qrot(Ci.q, ax);
+      if (type == 0) lin = cross3(Ci.t, ang);
       else { lin = ang; ang = mk3(0, 0, 0); }
       trow[3 * j + 0] = make_double2(lin.x, lin.y);
       trow[3 * j + 1] = make_double2(lin.z, ang.x);
       trow[3 * j + 2] = make_double2(ang.y, ang.z);
-      se3 O, L;
-      if (j == 0) O = O0;
+      se3 O;
+      qt oa;
+      if (j == 0) { O = O0; oa = O0a; }
       else {
         const double2 c0 = jc[0], c2 = jc[2], c3 = jc[3];
+        const double2 a0 = ((const double2*)s_oa)[2 * j], a1 = ((const double2*)s_oa)[2 * j + 1];
         O.t = mk3(c0.x, c0.y, c1.x);
         O.q.x = c2.x; O.q.y = c2.y; O.q.z = c3.x; O.q.w = c3.y;
+        oa.x = a0.x; oa.y = a0.y; oa.z = a1.x; oa.w = a1.y;
       }
       const double qj = qt_[j * T1_THREADS];
+      qt lq;  // conj(L_j.q)
+      v3 lt = O.t;
       if (type == 0) {
         double s, c;
         dsincos(0.5 * qj, s, c);
-        qt qa;
-        qa.x = ax.x * s; qa.y = ax.y * s; qa.z = ax.z * s; qa.w = c;
-        L.q = qmul(O.q, qa);
-        L.t = O.t;
+        lq.x = -fma(c, O.q.x, s * oa.x); lq.y = -fma(c, O.q.y, s * oa.y); lq.z = -fma(c, O.q.z, s * oa.z);
+        lq.w = fma(c, O.q.w, s * oa.w);
       } else {
-        L.q = O.q;
-        L.t = add3(O.t, qrot(O.q, scale3(ax, qj)));
+        lq = qconj(O.q);
+        lt = add3(O.t, qrot(O.q, scale3(ax, qj)));
       }
-      B = se3mul(L, B);
+      Ci.q = qmul(Ci.q, lq);
+      Ci.t = sub3(Ci.t, qrot(Ci.q, lt));
     }
+    se3 B;  // X = C_0^-1
+    B.q = qconj(Ci.q);
+    B.t = neg3(qrot(B.q, Ci.t));
     ErrCoef ec;
     v3 elin;
     error_terms(B.q, B.t, ec, elin);
@@ -355,7 +380,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
 extern "C" int optik_t1_smem_bytes(int n) {
   const size_t units = (size_t)((3 * n) | 1);
   return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * 2 * optik::T1_THREADS * units +
-               sizeof(double) * 3 * n * optik::T1_THREADS);
+               sizeof(double) * 3 * n * optik::T1_THREADS + sizeof(double) * 4 * n);
 }
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream) {
   const int smem = optik_t1_smem_bytes(p->n);

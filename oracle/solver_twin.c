@@ -341,8 +341,10 @@ int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const doub
 
 /* ======================= layout 1: thread-per-seed kernel (solve_t1_kernel.cu) =======================
  * Same objective, stop rules and LM step; sequential instead of lane-parallel evaluation order:
- *   - one BACKWARD recursion B_{j-1} = L_j B_j (B_n = tip) in the target's frame yields X = B_0 and, on the way,
- *     the body-Jacobian column of joint j from B_j:  [R_Bj^T (a_j x p_Bj) ; R_Bj^T a_j]
+ *   - one BACKWARD recursion in the target's frame on the INVERSE pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip):
+ *       column of joint j = [ t_C x (R_C a_j) ; R_C a_j ]  ( = [R_Bj^T (a_j x p_Bj) ; R_Bj^T a_j] ),
+ *       conj(L_j.q) = conj(cos * origin_q + sin * (origin_q (x) (a_j, 0))),
+ *       C.q <- C.q (x) conj(L_j.q),  C.t <- C.t - R_C.q(new) L_j.t ;   X = C_0^-1
  *   - Gram matrix and score are accumulated joint by joint with fma (no tree). */
 static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, const double* q, double* f, double* r,
                          double body[][6], err_coef* ec) {
@@ -350,33 +352,41 @@ static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, co
   se3t tgt_inv;
   tgt_inv.q = qt_conj(tgt.q);
   tgt_inv.t = v3_neg(qt_rot(tgt_inv.q, tgt.t));
-  se3t B = c->tip;
+  se3t C; /* tip^-1 */
+  C.q = qt_conj(c->tip.q);
+  C.t = v3_neg(qt_rot(C.q, c->tip.t));
   for (int j = n - 1; j >= 0; j--) {
     v3 ax = c->ax[j];
+    v3 ang = qt_rot(C.q, ax);
     if (c->type[j] == 0) {
-      v3 lin = qt_rot_inv(B.q, v3_cross(ax, B.t)), ang = qt_rot_inv(B.q, ax);
+      v3 lin = v3_cross(C.t, ang);
       body[j][0] = lin.x; body[j][1] = lin.y; body[j][2] = lin.z; body[j][3] = ang.x; body[j][4] = ang.y; body[j][5] = ang.z;
     } else {
-      v3 lin = qt_rot_inv(B.q, ax);
-      body[j][0] = lin.x; body[j][1] = lin.y; body[j][2] = lin.z; body[j][3] = 0; body[j][4] = 0; body[j][5] = 0;
+      body[j][0] = ang.x; body[j][1] = ang.y; body[j][2] = ang.z; body[j][3] = 0; body[j][4] = 0; body[j][5] = 0;
     }
-    se3t O, L;
+    se3t O;
     O.q = c->oq[j]; O.t = c->ot[j];
     if (j == 0) O = se3_mul(tgt_inv, O);
+    qt lq; /* conj(L.q) */
+    v3 lt = O.t;
     if (c->type[j] == 0) {
       double s, cs;
       tw_sincos(0.5 * q[j], &s, &cs);
-      qt qa = {ax.x * s, ax.y * s, ax.z * s, cs};
-      L.q = qt_mul(O.q, qa);
-      L.t = O.t;
+      qt axq = {ax.x, ax.y, ax.z, 0.0};
+      qt oa = qt_mul(O.q, axq);
+      lq.x = -fma(cs, O.q.x, s * oa.x); lq.y = -fma(cs, O.q.y, s * oa.y); lq.z = -fma(cs, O.q.z, s * oa.z);
+      lq.w = fma(cs, O.q.w, s * oa.w);
     } else {
-      L.q = O.q;
-      L.t = v3_add(O.t, qt_rot(O.q, v3_scale(ax, q[j])));
+      lq = qt_conj(O.q);
+      lt = v3_add(O.t, qt_rot(O.q, v3_scale(ax, q[j])));
     }
-    B = se3_mul(L, B);
+    C.q = qt_mul(C.q, lq);
+    C.t = v3_sub(C.t, qt_rot(C.q, lt));
   }
+  qt xq = qt_conj(C.q);
+  v3 xt = v3_neg(qt_rot(xq, C.t));
   v3 elin;
-  error_terms(B.q, B.t, ec, &elin);
+  error_terms(xq, xt, ec, &elin);
   v3 rl = elin, ra = ec->w;
   if (P->weighted) { rl = weight3(tgt.q, P->wl, elin); ra = weight3(tgt.q, P->wa, ec->w); }
   r[0] = rl.x; r[1] = rl.y; r[2] = rl.z; r[3] = ra.x; r[4] = ra.y; r[5] = ra.z;

@@ -1,0 +1,10 @@
+# quick loop for solver work: twin parity of every layout + the bench step
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -8
+timeout 600 python bench.py --steps 100 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; tail -3 gpurun_out/bench_iter.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_iter.json'))
+print('value %.4g ms/step %.4f e2e %.4g roof %.3f evals/s %.4g succ %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline_solve']['evals_per_s'], d['success_rate_per_attempt']), d['verified_equals_claimed'], d['oracle_spot_check_ok'])
+PY
