@@ -61,50 +61,93 @@ DEV double dot6(const double* a, const double* b) {
   return fma(a[0], b[0], fma(a[1], b[1], fma(a[2], b[2], fma(a[3], b[3], fma(a[4], b[4], a[5] * b[5])))));
 }
 
+// Polynomial coefficients live in constant memory: an fp64 instruction takes a constant-bank operand directly,
+// whereas a 64-bit literal costs two extra move instructions every time it is used (a third of dsincos was moves).
+static __constant__ double K_SC[20] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    6755399441055744.0,           // 1  1.5 * 2^52
+    1.57079632673412561417e+00,   // 2  pi/2, first 33 bits
+    6.07710050630396597660e-11,   // 3  next 33 bits
+    2.02226624871116645580e-21,   // 4  remainder
+    1.58969099521155010221e-10,   // 5  sin: S6
+    -2.50507602534068634195e-08,  // 6  S5
+    2.75573137070700676789e-06,   // 7  S4
+    -1.98412698298579493134e-04,  // 8  S3
+    8.33333333332248946124e-03,   // 9  S2
+    -1.66666666666666324348e-01,  // 10 S1
+    -1.13596475577881948265e-11,  // 11 cos: C6
+    2.08757232129817482790e-09,   // 12 C5
+    -2.75573143513906633035e-07,  // 13 C4
+    2.48015872894767294178e-05,   // 14 C3
+    -1.38888888888741095749e-03,  // 15 C2
+    4.16666666666666019037e-02,   // 16 C1
+    -0.5, 1.0, 0.0};
+static __constant__ double K_AT[18] = {
+    1.62858201153657823623e-02,   // 0  aT[10]
+    4.97687799461593236017e-02,   // 1  aT[8]
+    6.66107313738753120669e-02,   // 2  aT[6]
+    9.09088713343650656196e-02,   // 3  aT[4]
+    1.42857142725034663711e-01,   // 4  aT[2]
+    3.33333333333329318027e-01,   // 5  aT[0]
+    -3.65315727442169155270e-02,  // 6  aT[9]
+    -5.83357013379057348645e-02,  // 7  aT[7]
+    -7.69187620504482999495e-02,  // 8  aT[5]
+    -1.11111104054623557880e-01,  // 9  aT[3]
+    -1.99999999998764832476e-01,  // 10 aT[1]
+    4.63647609000806093515e-01,   // 11 atan(1/2) hi
+    2.26987774529616870924e-17,   // 12 atan(1/2) lo
+    7.85398163397448278999e-01,   // 13 pi/4 hi
+    3.06161699786838301793e-17,   // 14 pi/4 lo
+    1.57079632679489655800e+00,   // 15 pi/2 hi
+    6.12323399573676603587e-17,   // 16 pi/2 lo
+    0.0};
+
+// x with its sign bit XORed by `mask` (0 or 0x80000000): the same bits as a conditional negation, on the integer pipe
+DEV double dflip(double x, unsigned mask) { return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x)); }
+
 // sin/cos: Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4].
 DEV void dsincos(double x, double& sn, double& cs) {
   // k = rint(x * 2/pi) by the 1.5*2^52 shift (two fp64 adds instead of a round + a 64-bit convert, which run at a
   // quarter of the fp64 rate); the quadrant is the low two bits of the shifted value's mantissa.  Same result as
   // rint for |x * 2/pi| < 2^51; the CPU twin uses the identical sequence.
-  const double kk = x * 6.36619772367581382433e-01 + 6755399441055744.0;
-  const double k = kk - 6755399441055744.0;
-  double r = fma(-k, 1.57079632673412561417e+00, x);
-  r = fma(-k, 6.07710050630396597660e-11, r);
-  r = fma(-k, 2.02226624871116645580e-21, r);
+  const double kk = x * K_SC[0] + K_SC[1];
+  const double k = kk - K_SC[1];
+  double r = fma(-k, K_SC[2], x);
+  r = fma(-k, K_SC[3], r);
+  r = fma(-k, K_SC[4], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, K_SC[5], K_SC[6]);
+  ps = fma(z, ps, K_SC[7]);
+  ps = fma(z, ps, K_SC[8]);
+  ps = fma(z, ps, K_SC[9]);
+  ps = fma(z, ps, K_SC[10]);
   const double s = fma(r * z, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
-  const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const int q = __double2loint(kk) & 3;
-  double ss = (q & 1) ? c : s;
-  double cc = (q & 1) ? s : c;
-  if (q == 1 || q == 2) cc = -cc;
-  if (q >= 2) ss = -ss;
-  sn = ss;
-  cs = cc;
+  double pc = fma(z, K_SC[11], K_SC[12]);
+  pc = fma(z, pc, K_SC[13]);
+  pc = fma(z, pc, K_SC[14]);
+  pc = fma(z, pc, K_SC[15]);
+  pc = fma(z, pc, K_SC[16]);
+  const double c = fma(z * z, pc, fma(z, K_SC[17], K_SC[18]));
+  const unsigned q = (unsigned)__double2loint(kk);
+  const bool swap = (q & 1u) != 0u;
+  const double ss = swap ? c : s;
+  const double cc = swap ? s : c;
+  sn = dflip(ss, (q & 2u) << 30);         // quadrants 2, 3: -sin
+  cs = dflip(cc, ((q + 1u) & 2u) << 30);  // quadrants 1, 2: -cos
 }
 
 DEV double datan_poly(double x) {  // |x| <= 7/16
   const double z = x * x, w = z * z;
-  double s1 = fma(w, 1.62858201153657823623e-02, 4.97687799461593236017e-02);
-  s1 = fma(w, s1, 6.66107313738753120669e-02);
-  s1 = fma(w, s1, 9.09088713343650656196e-02);
-  s1 = fma(w, s1, 1.42857142725034663711e-01);
-  s1 = fma(w, s1, 3.33333333333329318027e-01);
+  double s1 = fma(w, K_AT[0], K_AT[1]);
+  s1 = fma(w, s1, K_AT[2]);
+  s1 = fma(w, s1, K_AT[3]);
+  s1 = fma(w, s1, K_AT[4]);
+  s1 = fma(w, s1, K_AT[5]);
   s1 = z * s1;
-  double s2 = fma(w, -3.65315727442169155270e-02, -5.83357013379057348645e-02);
-  s2 = fma(w, s2, -7.69187620504482999495e-02);
-  s2 = fma(w, s2, -1.11111104054623557880e-01);
-  s2 = fma(w, s2, -1.99999999998764832476e-01);
+  double s2 = fma(w, K_AT[6], K_AT[7]);
+  s2 = fma(w, s2, K_AT[8]);
+  s2 = fma(w, s2, K_AT[9]);
+  s2 = fma(w, s2, K_AT[10]);
   s2 = w * s2;
   return x - x * (s1 + s2);
 }
@@ -118,8 +161,8 @@ DEV double datan01(double t) {  // 0 <= t <= 1
   const double b = b1 ? 0.0 : 1.0;
   const double c = (b1 || !b2) ? 1.0 : 2.0;   // denominator c + d*t
   const double d = b1 ? 0.0 : 1.0;
-  const double hi = b1 ? 0.0 : (b2 ? 4.63647609000806093515e-01 : 7.85398163397448278999e-01);
-  const double lo = b1 ? 0.0 : (b2 ? 2.26987774529616870924e-17 : 3.06161699786838301793e-17);
+  const double hi = b1 ? 0.0 : (b2 ? K_AT[11] : K_AT[13]);
+  const double lo = b1 ? 0.0 : (b2 ? K_AT[12] : K_AT[14]);
   const double u = (a * t - b) / (c + d * t);
   return hi + (datan_poly(u) + lo);
 }
@@ -127,7 +170,7 @@ DEV double datan01(double t) {  // 0 <= t <= 1
 DEV double datan2_pos(double y, double x) {
   const bool small = y <= x;
   const double a = datan01(small ? y / x : x / y);
-  return small ? a : 1.57079632679489655800e+00 - (a - 6.12323399573676603587e-17);
+  return small ? a : K_AT[15] - (a - K_AT[16]);
 }
 
 // ---- ChaCha8 block (integer; restates rand_chacha's ChaCha8Rng state layout:
