@@ -234,28 +234,55 @@ def run_product(args):
     idx = np.where(st_h == 1)[0][:: max(1, int((st_h == 1).sum()) // 512)][:512]
     oracle_ok = all(ch.objective(q_h[i], tgt_h) < TOL_F and np.all(q_h[i] >= lb) and np.all(q_h[i] <= ub) for i in idx)
 
-    # ---- e2e: the same step through the public host-buffer API (H2D of target/x0, D2H of every record, per step)
-    def pinned(shape, dtype):
-        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
-    hrec = (pinned((R, n), torch.float64), pinned((R,), torch.float64), pinned((R,), torch.int32), pinned((R,), torch.int32))
-    tg_host = targets.cpu().numpy()
-    x0_host = 0.5 * (lb + ub)
+    # ---- e2e: the same step through the public host-buffer API (H2D of target/x0, D2H of every record, per step).
+    # Two legs: (a) one blocking call per step; (b) the headline: calls enqueued on two library streams with two sets
+    # of pinned buffers (OPTIK_BATCH_ASYNC), so one step's D2H overlaps the next step's kernels -- every step still
+    # copies its inputs from pinned host memory and its full records back, and the step's result is read on the host.
+    tg_host = ob.pinned_empty((K + W, 8))
+    tg_host[:] = targets.cpu().numpy()
+    x0_host = ob.pinned_empty(n)
+    x0_host[:] = 0.5 * (lb + ub)
     Ke = min(K, 50)
-    hrecord = pinned((obd.RECORD_HEAD + n,), torch.float64)
-    e2e_conv, e2e_times = 0, []
+    sets = [((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
+             ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)) for _ in range(2)]
+
+    def finish(k):
+        """host side of a step: wait for its stream, read the result (count converged records; cross-GPU best-pick)"""
+        hrec, hrecord, stream = sets[k]
+        stream.synchronize()
+        if world > 1:
+            robot.select_records(obd.all_gather_records(torch.from_numpy(hrecord).to(dev), out=gathered), out=best).cpu()
+        return int((hrec[2] == 1).sum())
+
+    # (a) blocking calls
+    sync_conv, sync_times = 0, []
     for s in range(3 + Ke):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        q, f, st, ev, b = robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile,
-                                            best=True, out=hrec, record=hrecord)
-        if world > 1:  # cross-GPU best-pick of the step's result, then back to the host
-            robot.select_records(obd.all_gather_records(torch.from_numpy(b).to(dev), out=gathered), out=best).cpu()
+        hrec, hrecord, stream = sets[0]
+        robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
+                          record=hrecord, stream=stream, wait=False)
+        c = finish(0)
         dt = time.perf_counter() - t0
         if s >= 3:
-            e2e_times.append(dt)
-            e2e_conv += int((st == 1).sum())
-    e2e_s = float(np.sum(e2e_times))
+            sync_times.append(dt)
+            sync_conv += c
+    # (b) pipelined, depth 2
+    if world > 1:
+        dist.barrier()
+    e2e_conv = 0
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        k = s & 1
+        if s >= 2:
+            e2e_conv += finish(k)
+        hrec, hrecord, stream = sets[k]
+        robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
+                          record=hrecord, stream=stream, wait=False)
+    for s in range(max(Ke - 2, 0), Ke):
+        e2e_conv += finish(s & 1)
+    e2e_s = time.perf_counter() - t0
     h2d = 8 * 8 + n * 8
     d2h = R * (n * 8 + 8 + 4 + 4) + (obd.RECORD_HEAD + n) * 8
 
@@ -301,13 +328,13 @@ def run_product(args):
         del rngq, tgB
 
     # ---- reduce over ranks
-    t = torch.tensor([dev_ms, e2e_s, t_wall], dtype=torch.float64, device=dev)
-    c = torch.tensor([verified, claimed, int(cnt[0]), int(cnt[1]), e2e_conv], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, t_wall, float(np.sum(sync_times))], dtype=torch.float64, device=dev)
+    c = torch.tensor([verified, claimed, int(cnt[0]), int(cnt[1]), e2e_conv, sync_conv], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_s, t_wall = [float(x) for x in t.cpu()]
-    verified, claimed, attempts, evals, e2e_conv = [float(x) for x in c.cpu()]
+    dev_ms, e2e_s, t_wall, sync_s = [float(x) for x in t.cpu()]
+    verified, claimed, attempts, evals, e2e_conv, sync_conv = [float(x) for x in c.cpu()]
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -324,7 +351,10 @@ def run_product(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, tile or 1),
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step_median": float(np.median(e2e_times) * 1e3), "api": "Robot.ik_attempts(host numpy buffers, pinned) -> optik_gpu_ik_attempts (C ABI)"},
+                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": 2,
+                    "api": "Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
+                           "OPTIK_BATCH_ASYNC (C ABI), two streams / two buffer sets; host reads every step's records",
+                    "blocking_call_value": sync_conv / sync_s, "blocking_call_ms_median": float(np.median(sync_times) * 1e3)},
             "gpu_launches": (3 if world == 1 else 4) * K,  # per step: solve_t1 + select (slice pass + final pass) [+ select_records]
             "roofline": roof,
             "roofline_solve": {"kernel": "solve_t1_kernel" if (tile or 1) == 1 else f"solve_kernel<{tile}>", "bound": "fp64 issue / latency (not HBM)",

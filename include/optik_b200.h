@@ -147,7 +147,16 @@ typedef struct optik_gpu_batch_opts {
    *   [3] cost f(q)  [4] status  [5..7] 0  [8..8+n) q
    * This is the record ranks exchange for a cross-GPU best-pick (optik_gpu_select_records). */
   double* best_record_out;
+  uint32_t flags;          /* OPTIK_BATCH_* bits */
+  uint32_t reserved;
 } optik_gpu_batch_opts;
+
+/* opts->flags.  OPTIK_BATCH_ASYNC (host-memory calls only, `stream` must be non-NULL): enqueue the H2D copies, the
+ * kernels and the D2H copies on `stream` and return WITHOUT waiting; outputs are valid after
+ * optik_gpu_stream_sync(stream).  Inputs and outputs must stay alive until then and should be pinned
+ * (optik_host_alloc), otherwise the copies are staged synchronously.  Two streams with two sets of buffers overlap
+ * one call's transfers with the next call's kernels.  opts->counters is then SET (not incremented). */
+#define OPTIK_BATCH_ASYNC 1u
 
 #define OPTIK_RECORD_HEAD 8
 
@@ -187,6 +196,12 @@ int optik_robot_ik_ex(const optik_robot* robot, const optik_solver_config* confi
  * restart index.  Device pointers, asynchronous on `stream`. */
 int optik_gpu_select_records(const optik_robot* robot, const double* records, uint32_t count, double* best_record_out,
                              void* stream);
+
+/* Streams for hosts without CUDA bindings of their own (Rust, ctypes): create on the robot's device, wait, destroy.
+ * Any cudaStream_t the caller already owns may be passed to the batched calls instead. */
+int optik_gpu_stream_create(const optik_robot* robot, void** stream_out);
+int optik_gpu_stream_sync(void* stream);
+void optik_gpu_stream_destroy(void* stream);
 
 /* Pinned host allocations for fast, truly asynchronous host<->device copies. */
 void* optik_host_alloc(uint64_t bytes);

@@ -39,7 +39,11 @@ class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
     _fields_ = [("struct_size", C.c_uint32), ("restarts", C.c_uint32), ("restart_begin", C.c_uint64),
                 ("chunks", C.c_uint32), ("tile", C.c_uint32), ("max_evals", C.c_uint32), ("blocks", C.c_uint32),
                 ("memory", C.c_int32), ("ee_offset", C.c_void_p), ("restart_out", C.c_void_p),
-                ("evals_out", C.c_void_p), ("counters", C.c_void_p), ("best_record_out", C.c_void_p)]
+                ("evals_out", C.c_void_p), ("counters", C.c_void_p), ("best_record_out", C.c_void_p),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+BATCH_ASYNC = 1  # == OPTIK_BATCH_ASYNC
 
 
 RECORD_HEAD = 8  # candidate record: [found, score, restart, cost, status, 0, 0, 0, q...]
@@ -89,6 +93,9 @@ def load_library():
         "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
         "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
         "optik_gpu_select_records": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "optik_gpu_stream_create": (C.c_int, [vp, C.POINTER(vp)]),
+        "optik_gpu_stream_sync": (C.c_int, [vp]),
+        "optik_gpu_stream_destroy": (None, [vp]),
         "optik_host_alloc": (vp, [C.c_uint64]),
         "optik_host_free": (None, [vp]),
     }
@@ -196,6 +203,66 @@ class SolverConfig:
 
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
+
+
+class Stream:
+    """A CUDA stream owned by the library (optik_gpu_stream_*), for pipelined host-buffer calls:
+    `robot.ik_attempts(..., stream=s, wait=False)` enqueues copies + kernels and returns; `s.synchronize()` waits.
+    A torch.cuda.Stream can be passed to the same arguments instead."""
+
+    def __init__(self, robot):
+        h = C.c_void_p()
+        _check(load_library().optik_gpu_stream_create(robot._h, C.byref(h)))
+        self.handle = h.value
+
+    def synchronize(self):
+        _check(load_library().optik_gpu_stream_sync(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load_library().optik_gpu_stream_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _stream_handle(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, Stream):
+        return stream.handle
+    if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
+        return stream.cuda_stream
+    return int(stream)
+
+
+class _PinnedBlock:
+    """Owner of one optik_host_alloc block; numpy views keep it alive through their .base chain."""
+
+    def __init__(self, nbytes):
+        self._lib = load_library()
+        self.ptr = self._lib.optik_host_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise OptikError(_err())
+        self.__array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.optik_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over pinned host memory (optik_host_alloc): copies to/from it are truly asynchronous."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    count = int(np.prod(shape))
+    nbytes = count * np.dtype(dtype).itemsize
+    raw = np.asarray(_PinnedBlock(nbytes))
+    return raw[:nbytes].view(dtype).reshape(shape)
 
 
 class Robot:
@@ -312,12 +379,14 @@ class Robot:
         return o, keep
 
     def ik_batch(self, config, targets, x0, restarts=None, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0,
-                 ee_offset=None, stats=False, out=None):
+                 ee_offset=None, stats=False, out=None, stream=None, wait=True):
         """Robot::ik over T (target, x0) pairs in one launch.
 
         targets: (T, 8) pose8 rows {qx,qy,qz,qw,tx,ty,tz,0};  x0: (T, n).
         numpy in  -> host path (H2D/D2H inside the call), returns numpy (q, cost, status[, extra]).
         torch CUDA tensors in -> device path on torch's current stream, returns torch tensors (no sync).
+        Host path with stream=<Stream> and wait=False: returns as soon as everything is enqueued; the outputs (give
+        pinned `out` buffers, see pinned_empty) are valid after stream.synchronize().
         """
         lib = load_library()
         c = config._c()
@@ -357,6 +426,11 @@ class Robot:
         else:
             q, f, st = out
         o, keep = self._opts(0, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
+        sh = _stream_handle(stream)
+        if not wait:
+            if sh is None:
+                raise ValueError("wait=False needs a stream")
+            o.flags |= BATCH_ASYNC
         extra = {}
         if stats:
             extra["restart"] = np.zeros(T, dtype=np.uint64)
@@ -364,16 +438,18 @@ class Robot:
             extra["counters"] = np.zeros(3, dtype=np.uint64)
             o.restart_out, o.evals_out, o.counters = extra["restart"].ctypes.data, extra["evals"].ctypes.data, extra["counters"].ctypes.data
         _check(lib.optik_gpu_ik_batch(self._h, C.byref(c), C.byref(o), targets.ctypes.data, x0.ctypes.data, T,
-                                      q.ctypes.data, f.ctypes.data, st.ctypes.data, None))
+                                      q.ctypes.data, f.ctypes.data, st.ctypes.data, sh))
         return (q, f, st, extra) if stats else (q, f, st)
 
     def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None,
-                    best=False, out=None, counters=None, record=None):
+                    best=False, out=None, counters=None, record=None, stream=None, wait=True):
         """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
         completion (no Speed-mode early exit) -- BASELINE config 2's output.  best=True also runs the selection
         pass (lib.rs:397-413) and appends the packed candidate record (RECORD_HEAD + n doubles:
         [found, score, restart, cost, status, 0,0,0, q...]).  numpy = host path (out = preallocated, e.g. pinned,
-        buffers), torch CUDA tensors = device path on the current stream (no host sync)."""
+        buffers), torch CUDA tensors = device path on the current stream (no host sync).  Host path with
+        stream=<Stream>, wait=False: enqueue only (target, x0 and the outputs must be pinned and stay alive);
+        results are valid after stream.synchronize()."""
         lib = load_library()
         c = config._c()
         n, R = self._n, int(restarts)
@@ -398,8 +474,17 @@ class Robot:
             _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.data_ptr(), x0.data_ptr(), q.data_ptr(),
                                              f.data_ptr(), st.data_ptr(), ev.data_ptr(), stream))
             return (q, f, st, ev, record) if best else (q, f, st, ev)
+        sh = _stream_handle(stream)
+        if not wait:
+            if sh is None or out is None:
+                raise ValueError("wait=False needs a stream and preallocated (pinned) out buffers")
+            o.flags |= BATCH_ASYNC
+            if not (isinstance(target, np.ndarray) and target.dtype == np.float64 and target.flags.c_contiguous
+                    and isinstance(x0, np.ndarray) and x0.dtype == np.float64 and x0.flags.c_contiguous):
+                raise ValueError("wait=False: target and x0 must be contiguous float64 arrays that outlive the call")
+        else:
+            x0 = self._x(x0)
         target = np.ascontiguousarray(target, dtype=np.float64).reshape(8)
-        x0 = self._x(x0)
         if out is None:
             out = (np.empty((R, n)), np.empty(R), np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32))
         q, f, st, ev = out
@@ -410,7 +495,7 @@ class Robot:
         if counters is not None:
             o.counters = counters.ctypes.data
         _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.ctypes.data, x0.ctypes.data,
-                                         q.ctypes.data, f.ctypes.data, st.ctypes.data, ev.ctypes.data, None))
+                                         q.ctypes.data, f.ctypes.data, st.ctypes.data, ev.ctypes.data, sh))
         return (q, f, st, ev, record) if best else (q, f, st, ev)
 
     def select_records(self, records, out=None):

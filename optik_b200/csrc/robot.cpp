@@ -504,6 +504,24 @@ void* optik_host_alloc(uint64_t bytes) {
 }
 void optik_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+int optik_gpu_stream_create(const optik_robot* robot, void** stream_out) {
+  if (!robot || !stream_out) return fail(OPTIK_ERR_INVALID, "null argument");
+  {
+    std::lock_guard<std::mutex> lk(robot->mu);
+    if (int rc = robot->ensure_gpu()) return rc;
+  }
+  CUDA_TRY(cudaSetDevice(robot->device));
+  cudaStream_t s = nullptr;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream_out = (void*)s;
+  return OPTIK_OK;
+}
+int optik_gpu_stream_sync(void* stream) {
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return OPTIK_OK;
+}
+void optik_gpu_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+
 // ---------------------------------------------------------------- batched evaluator
 int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double* targets, int shared_target,
                          uint64_t B, const double* linear_weight, const double* angular_weight,
@@ -605,10 +623,14 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   }
   const uint64_t r_begin = opts ? opts->restart_begin : 0;
   const int memory = opts ? opts->memory : 0;
+  const bool async = opts && (opts->flags & OPTIK_BATCH_ASYNC);
+  if (async && (memory == 1 || !stream))
+    return fail(OPTIK_ERR_INVALID, "OPTIK_BATCH_ASYNC is for host-memory calls on a caller-provided stream");
   std::unique_lock<std::mutex> lk(robot->mu);
   if (int rc = robot->ensure_gpu()) return rc;
   CUDA_TRY(cudaSetDevice(robot->device));
   cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
+  if (async) lk.unlock();  // own stream, stream-ordered scratch: nothing of the robot is mutated
   const int n = robot->n;
   const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(config->max_time * 1e9) : 0ull;
   const uint64_t NO = per_attempt ? R : T;  // number of output records
@@ -647,8 +669,9 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
     CUDA_TRY(cudaMemcpyAsync(opts->best_record_out, d + o_br, (OPTIK_RECORD_HEAD + n) * 8, cudaMemcpyDeviceToHost, s));
   if (evals_host) CUDA_TRY(cudaMemcpyAsync(evals_host, d + o_e, NO * 4, cudaMemcpyDeviceToHost, s));
   uint64_t cnt[3] = {0, 0, 0};
-  if (want_cnt) CUDA_TRY(cudaMemcpyAsync(cnt, d + o_c, 24, cudaMemcpyDeviceToHost, s));
+  if (want_cnt) CUDA_TRY(cudaMemcpyAsync(async ? opts->counters : cnt, d + o_c, 24, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaFreeAsync(d, s));
+  if (async) return OPTIK_OK;  // the caller waits with optik_gpu_stream_sync(stream)
   CUDA_TRY(cudaStreamSynchronize(s));
   if (want_cnt) for (int i = 0; i < 3; i++) opts->counters[i] += cnt[i];
   return OPTIK_OK;

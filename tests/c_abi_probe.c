@@ -9,6 +9,7 @@
 int main(int argc, char** argv) {
   if (argc < 4) return 2;
   if (sizeof(optik_solver_config) != 96) return 3; /* CSolverConfig layout, crates/optik-cpp/src/lib.rs:10-20 */
+  printf("sizeof(optik_gpu_batch_opts)=%u\n", (unsigned)sizeof(optik_gpu_batch_opts));
   optik_robot* r = optik_robot_from_urdf_file(argv[1], argv[2], argv[3]);
   if (!r) return 4;
   unsigned n = optik_robot_num_positions(r);

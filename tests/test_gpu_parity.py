@@ -447,3 +447,36 @@ def test_infinite_limits_chain_solves():
     assert (st == 1).sum() > 10
     for i in np.where(st == 1)[0][:8]:
         assert ch.objective(q[i], tgt) < 1e-6
+
+
+def test_async_host_calls_pipeline_and_match_sync():
+    """OPTIK_BATCH_ASYNC: two streams, two sets of pinned buffers, calls enqueued back to back -- same records as the
+    synchronous call, bit for bit."""
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(9)
+    R, n = 2048, ch.n
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    x0 = ob.pinned_empty(n)
+    x0[:] = 0.5 * (ch.lb + ch.ub)
+    tgts = ob.pinned_empty((4, 8))
+    tgts[:] = targets_for(ch, rng, 4)
+    streams = [ob.Stream(r), ob.Stream(r)]
+    bufs = [(ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32))
+            for _ in range(2)]
+    recs = [ob.pinned_empty(ob.RECORD_HEAD + n) for _ in range(2)]
+    got = []
+    for s in range(4):
+        k = s & 1
+        if s >= 2:
+            streams[k].synchronize()
+            got.append(tuple(a.copy() for a in bufs[k]) + (recs[k].copy(),))
+        r.ik_attempts(cfg, tgts[s], x0, R, best=True, out=bufs[k], record=recs[k], stream=streams[k], wait=False)
+    for k in (0, 1):
+        streams[k].synchronize()
+        got.append(tuple(a.copy() for a in bufs[k]) + (recs[k].copy(),))
+    for s in range(4):
+        q, f, st, ev, best = r.ik_attempts(cfg, np.array(tgts[s]), np.array(x0), R, best=True)
+        for a, b in zip(got[s], (q, f, st, ev, best)):
+            assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        r.ik_attempts(cfg, tgts[0], x0, R, out=bufs[0], wait=False)  # no stream

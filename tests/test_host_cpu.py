@@ -171,3 +171,5 @@ def test_header_is_valid_c_and_links(tmp_path):
     assert p.returncode == 0, p.stdout + p.stderr
     assert "n=7 joints=8 inside=1 lb0=-2.8973 ub0=2.8973" in p.stdout
     assert "EE link 'nope' does not exist" in p.stdout
+    # the ctypes mirror of optik_gpu_batch_opts has the C compiler's layout
+    assert f"sizeof(optik_gpu_batch_opts)={C.sizeof(ob._BatchOpts)}" in p.stdout

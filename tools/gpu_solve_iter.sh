@@ -6,5 +6,5 @@ timeout 600 python bench.py --steps 100 --no-cpu-baseline > gpurun_out/bench_ite
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_iter.json'))
-print('value %.4g ms/step %.4f e2e %.4g roof %.3f evals/s %.4g succ %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline_solve']['evals_per_s'], d['success_rate_per_attempt']), d['verified_equals_claimed'], d['oracle_spot_check_ok'])
+print('value %.4g ms/step %.4f e2e %.4g (blocking %.4g) roof %.3f evals/s %.4g succ %.3f' % (d['value'], d['ms_per_step'], d["e2e"]["value"], d["e2e"]["blocking_call_value"], d["roofline"]["frac"], d['roofline_solve']['evals_per_s'], d['success_rate_per_attempt']), d['verified_equals_claimed'], d['oracle_spot_check_ok'])
 PY
