@@ -185,6 +185,20 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
                          const double* ee_offset, int memory, double* ee_out, double* jac_out, double* f_out,
                          double* grad_out, void* stream);
 
+/* Batched Robot::diff_ik (crates/optik/src/lib.rs:101-239): for each configuration the LP
+ *   max alpha  s.t.  J_W(x0) v = alpha V_WE,  |v_i| <= v_max_i,  0 <= alpha <= 1
+ * solved exactly (closed form instead of the reference's interior-point solve; see csrc/diffik_kernel.cu).
+ *   x0 [B][n]; V_WE [B][6] world-frame twist [linear; angular] (or one twist when shared_V != 0);
+ *   v_max [B][n] (or one vector when shared_vmax != 0), every entry > 0
+ *   alpha_out [B], v_out [B][n], status_out [B]: 1 = solved, 0 = no solution (rank-deficient Jacobian == None)
+ * num_positions must be 6 (the reference's case) or 7; otherwise OPTIK_ERR_UNSUPPORTED.  memory: 0 host, 1 device. */
+int optik_gpu_diff_ik_batch(const optik_robot* robot, const double* x0, const double* V_WE, int shared_V,
+                            const double* v_max, int shared_vmax, uint64_t B, const double* ee_offset, int memory,
+                            double* alpha_out, double* v_out, int32_t* status_out, void* stream);
+/* Robot::diff_ik with the arguments the C wrapper drops (alpha, ee_offset).  1 = solved, 0 = none, <0 = -(error). */
+int optik_robot_diff_ik_ex(const optik_robot* robot, const double* x0, const double* V_WE, const double* v_max,
+                           const double* ee_offset_pose8, double* alpha_out, double* v_out);
+
 /* Robot::ik with the arguments the C wrapper drops (crates/optik/src/lib.rs:241-247): ee_offset and the returned cost.
  * target_pose8 / ee_offset_pose8 are pose8 (ee_offset may be NULL = identity).  Same max_time / max_restarts
  * semantics as optik_robot_ik.  Returns 1 = solution written to q_out[n], *cost_out; 0 = no solution; <0 = -(error). */

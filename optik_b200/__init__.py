@@ -93,6 +93,8 @@ def load_library():
         "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
         "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
         "optik_gpu_select_records": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "optik_gpu_diff_ik_batch": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_uint64, vp, C.c_int, vp, vp, vp, vp]),
+        "optik_robot_diff_ik_ex": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(C.c_double), vp]),
         "optik_gpu_stream_create": (C.c_int, [vp, C.POINTER(vp)]),
         "optik_gpu_stream_sync": (C.c_int, [vp]),
         "optik_gpu_stream_destroy": (None, [vp]),
@@ -359,10 +361,58 @@ class Robot:
         return (list(q), cost.value) if rc == 1 else None
 
     def diff_ik(self, x0, V_WE, v_max, ee_offset=None):
-        """Out of scope of this build; the C symbol exists and reports "no solution"."""
-        self._x(x0)
-        self._x(v_max, "v_max")
-        return None
+        """optik.pyi:39-49 / crates/optik-py/src/lib.rs:133-155: (alpha, v) or None."""
+        x0 = self._x(x0)
+        v_max = self._x(v_max, "v_max")
+        V = np.ascontiguousarray(V_WE, dtype=np.float64).ravel()
+        if V.shape[0] != 6:
+            raise ValueError("V_WE must have 6 entries [linear; angular]")
+        eo = None
+        if ee_offset is not None:
+            eo = np.ascontiguousarray(ee_offset, dtype=np.float64)
+            eo = _pose8_from_rows(eo) if eo.shape == (4, 4) else eo.ravel()
+        alpha = C.c_double(0.0)
+        v = np.zeros(self._n)
+        rc = load_library().optik_robot_diff_ik_ex(self._h, x0.ctypes.data, V.ctypes.data, v_max.ctypes.data,
+                                                   None if eo is None else eo.ctypes.data, C.byref(alpha), v.ctypes.data)
+        if rc < 0:
+            raise OptikError(_err())
+        return (alpha.value, [float(t) for t in v]) if rc == 1 else None
+
+    def diff_ik_batch(self, x0, V_WE, v_max, ee_offset=None):
+        """diff_ik over B configurations in one launch.  x0 (B, n); V_WE (B, 6) or (6,); v_max (B, n) or (n,).
+        numpy -> host path, returns numpy (alpha (B,), v (B, n), status (B,) 1 = solved / 0 = none);
+        torch CUDA tensors -> device path on the current stream."""
+        lib = load_library()
+        n = self._n
+        eo = None
+        if ee_offset is not None:
+            eo = np.ascontiguousarray(ee_offset, dtype=np.float64)
+            eo = _pose8_from_rows(eo) if eo.shape == (4, 4) else eo.ravel()
+        eop = None if eo is None else eo.ctypes.data
+        if _is_torch(x0):
+            import torch
+            B, dev = x0.shape[0], x0.device
+            for t in (x0, V_WE, v_max):
+                assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+            assert x0.shape == (B, n) and V_WE.shape in ((B, 6), (6,)) and v_max.shape in ((B, n), (n,))
+            alpha = torch.empty((B,), dtype=torch.float64, device=dev)
+            v = torch.empty((B, n), dtype=torch.float64, device=dev)
+            st = torch.empty((B,), dtype=torch.int32, device=dev)
+            _check(lib.optik_gpu_diff_ik_batch(self._h, x0.data_ptr(), V_WE.data_ptr(), int(V_WE.dim() == 1), v_max.data_ptr(),
+                                               int(v_max.dim() == 1), B, eop, 1, alpha.data_ptr(), v.data_ptr(), st.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+            return alpha, v, st
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        V = np.ascontiguousarray(V_WE, dtype=np.float64)
+        vm = np.ascontiguousarray(v_max, dtype=np.float64)
+        B = x0.shape[0]
+        if x0.shape != (B, n) or V.shape not in ((B, 6), (6,)) or vm.shape not in ((B, n), (n,)):
+            raise ValueError("x0 must be (B, n); V_WE (B, 6) or (6,); v_max (B, n) or (n,)")
+        alpha, v, st = np.zeros(B), np.zeros((B, n)), np.zeros(B, dtype=np.int32)
+        _check(lib.optik_gpu_diff_ik_batch(self._h, x0.ctypes.data, V.ctypes.data, int(V.ndim == 1), vm.ctypes.data,
+                                           int(vm.ndim == 1), B, eop, 0, alpha.ctypes.data, v.ctypes.data, st.ctypes.data, None))
+        return alpha, v, st
 
     # ---- batched additions --------------------------------------------------------------------
     def _opts(self, memory, restarts=0, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0, ee_offset=None):

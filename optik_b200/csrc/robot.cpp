@@ -30,6 +30,7 @@ extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n);
+extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stream);
 extern "C" int optik_eval_occupancy(int n, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
 extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm);
@@ -784,9 +785,73 @@ extern "C" double* optik_robot_ik(const optik_robot* robot, const optik_solver_c
   return nullptr;
 }
 
-extern "C" double* optik_robot_diff_ik(const optik_robot* robot, const double*, const double*, const double*) {
+// ---------------------------------------------------------------- diff_ik (lib.rs:101-239)
+extern "C" int optik_gpu_diff_ik_batch(const optik_robot* robot, const double* x0, const double* V_WE, int shared_V,
+                                       const double* v_max, int shared_vmax, uint64_t B, const double* ee_offset,
+                                       int memory, double* alpha_out, double* v_out, int32_t* status_out, void* stream) {
+  if (!robot || !x0 || !V_WE || !v_max || !alpha_out || !v_out || !status_out) return fail(OPTIK_ERR_INVALID, "null argument");
+  const int n = robot->n;
+  if (n != 6 && n != 7) return fail(OPTIK_ERR_UNSUPPORTED, "diff_ik supports num_positions 6 (the reference's case) and 7");
+  if (B == 0) return OPTIK_OK;
+  if (memory == 0) {
+    const uint64_t nv = shared_vmax ? (uint64_t)n : B * n;
+    for (uint64_t k = 0; k < nv; k++)
+      if (!(v_max[k] > 0.0)) return fail(OPTIK_ERR_INVALID, "v_max entries must be > 0");
+  }
+  std::unique_lock<std::mutex> lk(robot->mu);
+  if (int rc = robot->ensure_gpu()) return rc;
+  CUDA_TRY(cudaSetDevice(robot->device));
+  cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
+  if (memory == 1) lk.unlock();
+  DiffIkParams P{};
+  P.chain = (const double*)robot->chain_dev.p; P.n = n; P.chain_bytes = robot->chain_bytes;
+  P.B = B; P.shared_V = shared_V ? 1 : 0; P.shared_vmax = shared_vmax ? 1 : 0;
+  if (ee_offset) for (int i = 0; i < 8; i++) P.ee_offset[i] = ee_offset[i];
+  else pose8_identity(P.ee_offset);
+  const uint64_t nblk = (B + 127) / 128, cap = (uint64_t)robot->sm_count * 4;
+  const int blocks = (int)(nblk < cap ? nblk : cap);
+  if (memory == 1) {
+    P.x0 = x0; P.V = V_WE; P.vmax = v_max; P.alpha_out = alpha_out; P.v_out = v_out; P.status_out = status_out;
+    CUDA_TRY(optik_launch_diffik(&P, blocks, s));
+    return OPTIK_OK;
+  }
+  size_t bytes = 0;
+  auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
+  const uint64_t nV = shared_V ? 6 : 6 * B, nm = shared_vmax ? (uint64_t)n : B * n;
+  const size_t o_x = carve(B * n * 8), o_V = carve(nV * 8), o_m = carve(nm * 8), o_a = carve(B * 8), o_v = carve(B * n * 8),
+               o_s = carve(B * 4);
+  char* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_x, x0, B * n * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_V, V_WE, nV * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_m, v_max, nm * 8, cudaMemcpyHostToDevice, s));
+  P.x0 = (double*)(d + o_x); P.V = (double*)(d + o_V); P.vmax = (double*)(d + o_m);
+  P.alpha_out = (double*)(d + o_a); P.v_out = (double*)(d + o_v); P.status_out = (int*)(d + o_s);
+  CUDA_TRY(optik_launch_diffik(&P, blocks, s));
+  CUDA_TRY(cudaMemcpyAsync(alpha_out, d + o_a, B * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(v_out, d + o_v, B * n * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, B * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(d, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return OPTIK_OK;
+}
+
+extern "C" int optik_robot_diff_ik_ex(const optik_robot* robot, const double* x0, const double* V_WE, const double* v_max,
+                                      const double* ee_offset_pose8, double* alpha_out, double* v_out) {
+  if (!robot) return -fail(OPTIK_ERR_INVALID, "null robot");
+  int32_t st = 0;
+  if (int rc = optik_gpu_diff_ik_batch(robot, x0, V_WE, 1, v_max, 1, 1, ee_offset_pose8, 0, alpha_out, v_out, &st, nullptr))
+    return -rc;
+  return st == 1 ? 1 : 0;
+}
+
+// crates/optik-cpp/src/lib.rs:164-183: n doubles (caller frees) or NULL when there is no solution; alpha is dropped
+extern "C" double* optik_robot_diff_ik(const optik_robot* robot, const double* x0, const double* V_WE, const double* v_max) {
   if (!robot) panic("called `Option::unwrap()` on a `None` value (null robot)");
-  static bool warned = false;
-  if (!warned) { warned = true; fprintf(stderr, "optik_b200: diff_ik is outside the scope of this build (returns no solution)\n"); }
-  return nullptr;
+  double alpha = 0.0;
+  double* v = (double*)malloc(sizeof(double) * robot->n);
+  const int rc = optik_robot_diff_ik_ex(robot, x0, V_WE, v_max, nullptr, &alpha, v);
+  if (rc < 0) { free(v); panic("diff_ik: " + g_last_error); }
+  if (rc == 0) { free(v); return nullptr; }
+  return v;
 }

@@ -113,3 +113,18 @@ struct EvalParams {
   double* f_out;     // [B] objective (objective.rs:40-57), may be null
   double* grad_out;  // [B][n] gradient (objective.rs:60-110), may be null
 };
+
+struct DiffIkParams {
+  const double* chain;
+  int n;                 // 6 or 7
+  uint32_t chain_bytes;
+  const double* x0;      // [B][n]
+  const double* V;       // [B][6] world-frame twist [linear; angular], or one shared twist
+  const double* vmax;    // [B][n] or one shared vector
+  int shared_V, shared_vmax;
+  unsigned long long B;
+  double ee_offset[8];
+  double* alpha_out;     // [B]
+  double* v_out;         // [B][n]
+  int* status_out;       // [B] 1 = solved, 0 = no solution (rank-deficient Jacobian)
+};

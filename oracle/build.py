@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_build", "liboptik_oracle.so")
-SRCS = [os.path.join(HERE, f) for f in ("optik_oracle.c", "solver_twin.c", "ref_loop.c")]
+SRCS = [os.path.join(HERE, f) for f in ("optik_oracle.c", "solver_twin.c", "ref_loop.c", "diffik_oracle.c")]
 
 
 def build(force: bool = False) -> str:

@@ -109,6 +109,17 @@ class Chain:
                                     _p(None if ee_offset is None else _d(ee_offset)), _p(_d(wl)), _p(_d(wa)), _p(g))
         return g
 
+    # crates/optik/src/lib.rs:123-239 (the LP solved exactly, see diffik_oracle.c)
+    def diff_ik(self, x0, V_WE, v_max, ee_offset=None):
+        """-> (alpha, v) or None (rank-deficient Jacobian)."""
+        alpha = C.c_double(0.0)
+        v = np.zeros(self.n)
+        rc = lib().oracle_diff_ik(_p(self.arr), self.njoints, _p(None if ee_offset is None else _d(ee_offset)), _p(_d(x0)),
+                                  _p(_d(V_WE)), _p(_d(v_max)), C.byref(alpha), _p(v))
+        if rc < 0:
+            raise ValueError(f"oracle_diff_ik: unsupported input ({rc})")
+        return (alpha.value, v) if rc == 1 else None
+
     def restart_seed(self, restart):
         q = np.zeros(self.n)
         lib().oracle_restart_seed(int(restart), _p(self.lb), _p(self.ub), self.n, _p(q))

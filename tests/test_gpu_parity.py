@@ -480,3 +480,87 @@ def test_async_host_calls_pipeline_and_match_sync():
             assert np.array_equal(a, b)
     with pytest.raises(ValueError):
         r.ik_attempts(cfg, tgts[0], x0, R, out=bufs[0], wait=False)  # no stream
+
+
+# ------------------------------------------------------------------ diff_ik (lib.rs:101-239)
+def test_diff_ik_matches_lp_golden_and_oracle():
+    """CUDA diff_ik vs the HiGHS-solved LP fixtures (alpha unique; v unique for 6 DOF) and vs the oracle's exact
+    solution on the same inputs (tolerance 1e-9: fp64, different but equivalent FK formulas)."""
+    import json, os
+    from conftest import ROOT
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "diff_ik_vectors.json")))["cases"]
+    robots = {name: robot_and_chain(name) for name in ("ur3e", "panda")}
+    for c in cases:
+        r, ch = robots[c["robot"]]
+        res = r.diff_ik(c["x0"], c["V_WE"], c["v_max"])
+        assert res is not None
+        alpha, v = res
+        assert abs(alpha - c["alpha"]) <= 1e-8
+        if c["v"] is not None:
+            assert np.abs(np.array(v) - np.array(c["v"])).max() <= 1e-8
+        oa, ov = ch.diff_ik(c["x0"], c["V_WE"], c["v_max"])
+        assert abs(alpha - oa) <= 1e-9 * max(1.0, abs(oa)) and np.abs(np.array(v) - ov).max() <= 1e-9 * max(1.0, np.abs(ov).max())
+
+
+@pytest.mark.parametrize("name", ["ur3e", "ur5", "panda"])
+def test_diff_ik_batch_properties(name):
+    """tests/test_ik.rs:184-209 at batch size (ragged B): alpha in [0,1], |v| <= vmax, J_W v = alpha V (the reference's
+    TODO), checked for every configuration; a sample against the oracle; shared and per-row V / vmax agree."""
+    import torch
+    r, ch = robot_and_chain(name)
+    rng = np.random.default_rng(7)
+    B, n = 4099, ch.n
+    x0 = rng.uniform(ch.lb, ch.ub, size=(B, n))
+    V = rng.random((B, 6))
+    vmax = rng.uniform(0.2, 2.0, size=(B, n))
+    alpha, v, st = r.diff_ik_batch(x0, V, vmax)
+    ok = st == 1
+    assert ok.mean() > 0.999
+    assert np.all(alpha[ok] >= 0) and np.all(alpha[ok] <= 1 + 1e-12)
+    assert np.all(np.abs(v[ok]) <= vmax[ok] * (1 + 1e-12))
+    out = r.eval_batch(x0, want=("ee", "jac"))
+    Jb = out["jac"].reshape(B, n, 6)  # column-major 6 x n per row
+    ee = out["ee"]
+    def rot(q, u):
+        w, uv = q[:, 3:4], q[:, :3]
+        t = 2.0 * np.cross(uv, u)
+        return u + w * t + np.cross(uv, t)
+    tw = np.einsum("bnk,bn->bk", Jb, v)  # body-frame twist J v
+    tw_w = np.concatenate([rot(ee, tw[:, :3]), rot(ee, tw[:, 3:])], axis=1)
+    resid = np.abs(tw_w - alpha[:, None] * V)[ok].max(axis=1)
+    assert np.quantile(resid, 0.99) < 1e-9 and resid.max() < 1e-6  # near-singular rows amplify rounding
+    for i in range(0, B, 257):
+        oa, ov = ch.diff_ik(x0[i], V[i], vmax[i])
+        assert abs(alpha[i] - oa) <= 1e-8 * max(1.0, abs(oa))
+        if n == 6:
+            assert np.abs(v[i] - ov).max() <= 1e-7 * max(1.0, np.abs(ov).max())
+    # device path, shared twist and shared vmax
+    a2, v2, s2 = r.diff_ik_batch(torch.from_numpy(x0).cuda(), torch.from_numpy(V[0]).cuda(), torch.from_numpy(vmax[0]).cuda())
+    a3, v3, s3 = r.diff_ik_batch(x0, np.tile(V[0], (B, 1)), np.tile(vmax[0], (B, 1)))
+    assert np.array_equal(a2.cpu().numpy(), a3) and np.array_equal(v2.cpu().numpy(), v3) and np.array_equal(s2.cpu().numpy(), s3)
+
+
+def test_diff_ik_edge_cases():
+    r, ch = robot_and_chain("ur3e")
+    # wrist singularity: no solution (None), through every entry point
+    x0 = np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])
+    V = [0.3, 0.1, 0.2, 0.5, 0.4, 0.6]
+    assert r.diff_ik(x0, V, np.ones(6)) is None and ch.diff_ik(x0, V, np.ones(6)) is None
+    import ctypes as C
+    lib = ob.load_library()
+    arr = lambda a: (C.c_double * len(a))(*a)
+    assert not lib.optik_robot_diff_ik(r._h, arr(x0), arr(V), arr([1.0] * 6))
+    p = lib.optik_robot_diff_ik(r._h, arr([0.3, -1.0, 1.2, 0.4, 0.7, 0.2]), arr(V), arr([1.0] * 6))
+    assert p
+    v = ob._take(p, 6)
+    assert np.all(np.abs(v) <= 1 + 1e-12)
+    # zero twist: alpha = 1, v = 0; empty batch; bad v_max; unsupported size
+    a, v0 = r.diff_ik([0.3, -1.0, 1.2, 0.4, 0.7, 0.2], np.zeros(6), np.ones(6))
+    assert a == 1.0 and np.all(np.array(v0) == 0)
+    a, vv, st = r.diff_ik_batch(np.zeros((0, 6)), np.zeros(6), np.ones(6))
+    assert a.shape == (0,) and vv.shape == (0, 6)
+    with pytest.raises(ob.OptikError):
+        r.diff_ik_batch(np.zeros((1, 6)), np.zeros(6), np.zeros(6))
+    snake, _ = robot_and_chain("snake20")
+    with pytest.raises(ob.OptikError):
+        snake.diff_ik_batch(np.zeros((1, 20)), np.zeros(6), np.ones(20))
