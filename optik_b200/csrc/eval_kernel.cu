@@ -65,26 +65,30 @@ DEV void e_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
 
 // N = compile-time joint count (fully unrolled joint loops: static shared-memory offsets, the scheduler overlaps one
 // joint's sin/cos with the previous joint's quaternion chain); N = 0 reads n from the parameters.
-template <int N>
+// COLS = Jacobian columns are needed (jac_out or grad_out): per-thread rows in shared memory, ONE tile buffer per warp
+// (refilled while the warp forms objective / gradient / stores).  COLS = false is the FK-only launch: no rows, TWO
+// tile buffers per warp, the next tile is requested before the current one is consumed.
+template <int N, bool COLS>
 __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_constant__ EvalParams P) {
   extern __shared__ __align__(128) double smem[];
-  // layout: chain blob | block mbarrier (16 B) | one mbarrier per warp (8 B each) | per-thread Jacobian rows |
-  //         per-warp joint-vector tiles [EVAL_WARPS][32 * n] | per-joint constants origin_q (x) axis [n][4]
+  // layout: chain blob | block mbarrier (16 B) | two mbarriers per warp (8 B each) | per-thread Jacobian rows (COLS) |
+  //         per-warp joint-vector tiles [EVAL_WARPS][NBUF][32 * n] | per-joint constants origin_q (x) axis [n][4]
+  constexpr int NBUF = COLS ? 1 : 2;
   double* s_chain = smem;
   const int n = N ? N : P.n;
   const int chain_doubles = OPTIK_CHAIN_STRIDE * n + 8;
   uint64_t* s_bar = (uint64_t*)(smem + chain_doubles);
   uint64_t* s_wbar = (uint64_t*)(smem + chain_doubles + 2);
-  double2* s_rows = (double2*)(smem + chain_doubles + 2 + EVAL_WARPS);
+  double2* s_rows = (double2*)(smem + chain_doubles + 2 + 2 * EVAL_WARPS);
   const int units = eval_row_units(n);
-  double* s_q = (double*)(s_rows + (size_t)EVAL_THREADS * units);
-  double2* s_oa = (double2*)(s_q + (size_t)EVAL_WARPS * 32 * n);  // [n][2]
+  double* s_q = (double*)(s_rows + (COLS ? (size_t)EVAL_THREADS * units : 0));
+  double2* s_oa = (double2*)(s_q + (size_t)EVAL_WARPS * NBUF * 32 * n);  // [n][2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_bar)));
 #pragma unroll
-    for (int w = 0; w < EVAL_WARPS; w++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_wbar + w)));
+    for (int w = 0; w < 2 * EVAL_WARPS; w++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_wbar + w)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -94,24 +98,25 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
   // shared memory with one TMA bulk load per tile; the load of tile k+1 is issued as soon as the recursion of tile k
   // has consumed the buffer and lands while the warp forms objective / gradient / stores of tile k.  No thread ever
   // waits on a dependent global load of q inside the joint loop.  Ragged last tile / unaligned q: plain loads.
-  double* qb = s_q + (size_t)warp * 32 * n;
-  const uint32_t qb_addr = e_smem_u32(qb), wbar = e_smem_u32(s_wbar + warp);
+  double* const qb0 = s_q + (size_t)warp * NBUF * 32 * n;  // buffer b at qb0 + b * 32 * n, barrier b at wbar0 + 8 b
+  const uint32_t wbar0 = e_smem_u32(s_wbar + 2 * warp);
   const uint32_t tile_bytes = 256u * (uint32_t)n;
   const bool q_aligned = (((unsigned long long)P.q) & 15ull) == 0ull;
   const unsigned long long stride = (unsigned long long)gridDim.x * EVAL_THREADS;
   unsigned long long base = (unsigned long long)blockIdx.x * EVAL_THREADS + 32ull * warp;  // first configuration of my tile
-  uint32_t parity = 0;
-  bool pending = false;
-  auto fetch_tile = [&](unsigned long long b) {
+  uint32_t parity = 0, pending = 0;  // bit b: phase parity of barrier b / a bulk load into buffer b is in flight
+  auto fetch_tile = [&](unsigned long long b, int buf) {
+    double* qb = qb0 + buf * 32 * n;
     if (q_aligned && b + 32 <= P.B) {
-      if (lane == 0) e_bulk_load(qb_addr, P.q + b * n, tile_bytes, wbar);
-      return true;
+      if (lane == 0) e_bulk_load(e_smem_u32(qb), P.q + b * n, tile_bytes, wbar0 + 8u * buf);
+      pending |= 1u << buf;
+      return;
     }
     if (b + lane < P.B)
       for (int j = 0; j < n; j++) qb[lane * n + j] = P.q[(b + lane) * n + j];
-    return false;
   };
-  if (base < P.B) pending = fetch_tile(base);
+  if (base < P.B) fetch_tile(base, 0);
+  int buf = 0;
   e_mbar_wait(e_smem_u32(s_bar), 0);  // chain staged
 
   if (threadIdx.x < n) {  // per-joint constant origin_q (x) (axis, 0)
@@ -129,13 +134,14 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
   tip_inv.q = qconj(tip.q);
   tip_inv.t = neg3(qrot(tip_inv.q, tip.t));
   const bool want_obj = (P.f_out != nullptr) || (P.grad_out != nullptr);
-  const bool want_cols = (P.jac_out != nullptr) || (P.grad_out != nullptr);
+  constexpr bool want_cols = COLS;
   double2* my = s_rows + (size_t)threadIdx.x * units;
   const uint32_t my_addr = e_smem_u32(my);
   const uint32_t row_bytes = 48u * (uint32_t)n;
-  const double* q = qb + lane * n;
 
   for (; base < P.B; base += stride) {
+    const double* q = qb0 + buf * 32 * n + lane * n;
+    if (NBUF == 2 && base + stride < P.B) fetch_tile(base + stride, buf ^ 1);  // consumed one iteration ago
     const unsigned long long i = base + lane;
     const bool active = i < P.B;
     // my previous row must have been read out by the TMA before it is overwritten
@@ -146,7 +152,11 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
       const double2* tp = (const double2*)(P.targets + (unsigned long long)P.target_stride * i);
       t0 = tp[0]; t1 = tp[1]; t2 = tp[2]; t3 = tp[3];
     }
-    if (pending) { e_mbar_wait(wbar, parity); parity ^= 1u; }
+    if (pending & (1u << buf)) {
+      e_mbar_wait(wbar0 + 8u * buf, (parity >> buf) & 1u);
+      parity ^= 1u << buf;
+      pending &= ~(1u << buf);
+    }
     // Backward recursion on the INVERSE pose C_j = B_j^-1 = (R_B^T, -R_B^T p_B): the column of joint j is then
     //   ang = R_C axis_j ,  lin = t_C x ang      [ = R_B^T (axis_j x p_B) ]
     // (one rotation + one cross product instead of two rotations), and  C_{j-1} = C_j L_j^-1  with
@@ -192,7 +202,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
     B.t = neg3(qrot(B.q, Cinv.t));
     // the tile buffer is free once every lane has finished its recursion: stream the warp's next tile into it
     __syncwarp();
-    pending = (base + stride < P.B) ? fetch_tile(base + stride) : false;
+    if (NBUF == 1) { if (base + stride < P.B) fetch_tile(base + stride, 0); }
+    else buf ^= 1;
     if (!active) continue;
     if (P.jac_out) {  // hand the staged row to the TMA: 48n contiguous bytes of HBM per configuration
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -274,33 +285,34 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
 
 }  // namespace optik
 
-extern "C" int optik_eval_smem_bytes(int n);
-static const void* eval_entry(int n) {
+static const void* eval_entry(int n, bool cols) {
   switch (n) {
-    case 6: return (const void*)optik::eval_kernel<6>;
-    case 7: return (const void*)optik::eval_kernel<7>;
-    default: return (const void*)optik::eval_kernel<0>;
+    case 6: return cols ? (const void*)optik::eval_kernel<6, true> : (const void*)optik::eval_kernel<6, false>;
+    case 7: return cols ? (const void*)optik::eval_kernel<7, true> : (const void*)optik::eval_kernel<7, false>;
+    default: return cols ? (const void*)optik::eval_kernel<0, true> : (const void*)optik::eval_kernel<0, false>;
   }
 }
+extern "C" int optik_eval_smem_bytes(int n, int cols) {
+  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2 + 2 * optik::EVAL_WARPS) +
+               (cols ? 16ull * optik::EVAL_THREADS * (size_t)((3 * n) | 1) : 0ull) +
+               sizeof(double) * 32ull * n * optik::EVAL_WARPS * (cols ? 1 : 2) + sizeof(double) * 4ull * n);
+}
+static bool eval_wants_cols(const EvalParams* p) { return p->jac_out != nullptr || p->grad_out != nullptr; }
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream) {
-  const size_t smem = (size_t)optik_eval_smem_bytes(p->n);
-  const void* fn = eval_entry(p->n);
+  const bool cols = eval_wants_cols(p);
+  const size_t smem = (size_t)optik_eval_smem_bytes(p->n, cols);
+  const void* fn = eval_entry(p->n, cols);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   void* args[] = {(void*)p};
   e = cudaLaunchKernel(fn, dim3(blocks), dim3(optik::EVAL_THREADS), args, smem, (cudaStream_t)stream);
   return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
-extern "C" int optik_eval_smem_bytes(int n) {
-  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2 + optik::EVAL_WARPS) +
-               16ull * optik::EVAL_THREADS * (size_t)((3 * n) | 1) + sizeof(double) * 32ull * n * optik::EVAL_WARPS +
-               sizeof(double) * 4ull * n);
-}
 // resident blocks per SM: the kernel is persistent (grid-stride over tiles), so the launcher sizes the grid to
 // exactly sm_count * this
-extern "C" int optik_eval_occupancy(int n, int* blocks_per_sm) {
-  const int smem = optik_eval_smem_bytes(n);
-  const void* fn = eval_entry(n);
+extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm) {
+  const int smem = optik_eval_smem_bytes(n, cols);
+  const void* fn = eval_entry(n, cols != 0);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, optik::EVAL_THREADS, smem);

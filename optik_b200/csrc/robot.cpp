@@ -29,9 +29,9 @@ extern "C" int optik_launch_select(const SelectParams* p, unsigned slices, void*
 extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
-extern "C" int optik_eval_smem_bytes(int n);
+extern "C" int optik_eval_smem_bytes(int n, int cols);
 extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stream);
-extern "C" int optik_eval_occupancy(int n, int* blocks_per_sm);
+extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
 extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm);
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
@@ -536,7 +536,8 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
   if (int rc = robot->ensure_gpu()) return rc;
   CUDA_TRY(cudaSetDevice(robot->device));
   const int n = robot->n;
-  if (optik_eval_smem_bytes(n) > 227 * 1024) return fail(OPTIK_ERR_UNSUPPORTED, "chain too long for the evaluator tile");
+  const int cols = (jac_out || grad_out) ? 1 : 0;
+  if (optik_eval_smem_bytes(n, cols) > 227 * 1024) return fail(OPTIK_ERR_UNSUPPORTED, "chain too long for the evaluator tile");
   // device-pointer calls run on the caller's stream (NULL = the legacy default stream); host-pointer calls on ours
   cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
   if (memory == 1) lk.unlock();  // device-pointer calls only touch immutable robot state
@@ -552,11 +553,11 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
   if (ee_offset) for (int i = 0; i < 8; i++) P.ee_offset[i] = ee_offset[i];
   else pose8_identity(P.ee_offset);
   // persistent grid: one wave of resident blocks, each striding over tiles of 128 configurations
-  static std::atomic<int> occ_cache[OPTIK_MAX_DOF + 1];  // blocks/SM per n (all GPUs of a box are alike)
-  int per_sm = occ_cache[n].load(std::memory_order_relaxed);
+  static std::atomic<int> occ_cache[2][OPTIK_MAX_DOF + 1];  // blocks/SM per (layout, n) (all GPUs of a box are alike)
+  int per_sm = occ_cache[cols][n].load(std::memory_order_relaxed);
   if (per_sm == 0) {
-    CUDA_TRY(optik_eval_occupancy(n, &per_sm));
-    occ_cache[n].store(per_sm, std::memory_order_relaxed);
+    CUDA_TRY(optik_eval_occupancy(n, cols, &per_sm));
+    occ_cache[cols][n].store(per_sm, std::memory_order_relaxed);
   }
   if (per_sm < 1) return fail(OPTIK_ERR_UNSUPPORTED, "evaluator tile does not fit one SM");
   const uint64_t nblk = (B + 127) / 128, resident = (uint64_t)robot->sm_count * (uint64_t)per_sm;
