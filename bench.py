@@ -268,20 +268,40 @@ def run_product(args):
         if s >= 3:
             sync_times.append(dt)
             sync_conv += c
-    # (b) pipelined, depth 2
+    # (b) pipelined, depth 2.  One GPU: the C ABI's asynchronous host-buffer call.  Several GPUs: the same step with the
+    # all-gather + global best-pick enqueued on the step's stream (optik_b200.dist.HostStepPipeline), so no rank blocks
+    # on a collective between steps.
     if world > 1:
         dist.barrier()
     e2e_conv = 0
-    t0 = time.perf_counter()
-    for s in range(Ke):
-        k = s & 1
-        if s >= 2:
-            e2e_conv += finish(k)
-        hrec, hrecord, stream = sets[k]
-        robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
-                          record=hrecord, stream=stream, wait=False)
-    for s in range(max(Ke - 2, 0), Ke):
-        e2e_conv += finish(s & 1)
+    if world == 1:
+        t0 = time.perf_counter()
+        for s in range(Ke):
+            k = s & 1
+            if s >= 2:
+                e2e_conv += finish(k)
+            hrec, hrecord, stream = sets[k]
+            robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
+                              record=hrecord, stream=stream, wait=False)
+        for s in range(max(Ke - 2, 0), Ke):
+            e2e_conv += finish(s & 1)
+    else:
+        pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=2, device=dev)
+        for s in range(2):  # warm the slots (NCCL stream setup)
+            pipe.submit(s, tg_host[W], x0_host)
+        for s in range(2):
+            pipe.result(s)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for s in range(Ke):
+            k = s & 1
+            if s >= 2:
+                r_ = pipe.result(k)
+                e2e_conv += int((r_[2] == 1).sum()) * int(r_[4][0] >= 0)
+            pipe.submit(k, tg_host[W + (s % K)], x0_host)
+        for s in range(max(Ke - 2, 0), Ke):
+            r_ = pipe.result(s & 1)
+            e2e_conv += int((r_[2] == 1).sum()) * int(r_[4][0] >= 0)
     e2e_s = time.perf_counter() - t0
     h2d = 8 * 8 + n * 8
     d2h = R * (n * 8 + 8 + 4 + 4) + (obd.RECORD_HEAD + n) * 8
@@ -352,8 +372,12 @@ def run_product(args):
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": 2,
-                    "api": "Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
-                           "OPTIK_BATCH_ASYNC (C ABI), two streams / two buffer sets; host reads every step's records",
+                    "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
+                            "OPTIK_BATCH_ASYNC (C ABI), two streams / two buffer sets; host reads every step's records"
+                            if world == 1 else
+                            "optik_b200.dist.HostStepPipeline: per step H2D from pinned buffers -> optik_gpu_ik_attempts "
+                            "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
+                            "the records and the global best, all on the step's stream; two steps in flight"),
                     "blocking_call_value": sync_conv / sync_s, "blocking_call_ms_median": float(np.median(sync_times) * 1e3)},
             "gpu_launches": (3 if world == 1 else 4) * K,  # per step: solve_t1 + select (slice pass + final pass) [+ select_records]
             "roofline": roof,

@@ -95,3 +95,53 @@ def ik_batch_target_sharded(robot, config, targets, x0, restarts, rank=0, world=
     out = torch.empty((world * rec.shape[0], n + 2), dtype=torch.float64, device=rec.device)
     dist.all_gather_into_tensor(out, rec, group=group)  # equal shard sizes required
     return out[:, :n], out[:, n], out[:, n + 1].to(torch.int32)
+
+
+class HostStepPipeline:
+    """Host-buffer steps of ik_restart_sharded with the cross-GPU best-pick INSIDE the step, `depth` steps in flight.
+
+    Each slot owns a CUDA stream, device staging and pinned host buffers; submit() enqueues, on the slot's stream:
+    H2D of (target, x0) from pinned memory -> solve + select (C ABI, device path) -> one NCCL all-gather of the
+    candidate record -> select_records -> D2H of this rank's per-restart records and of the global best record.
+    Nothing blocks the host until result(slot).  With world == 1 the all-gather is skipped."""
+
+    def __init__(self, robot, config, restarts_per_rank, rank=0, world=1, group=None, tile=0, depth=2, device=None):
+        import torch
+        self.robot, self.config, self.R, self.rank, self.world, self.group, self.tile = robot, config, int(restarts_per_rank), rank, world, group, tile
+        n = robot.num_positions()
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.slots = []
+        for _ in range(depth):
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            d = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            self.slots.append({
+                "stream": torch.cuda.Stream(device=dev),
+                "h_in": (pin((8,), torch.float64), pin((n,), torch.float64)),
+                "d_in": (d((8,), torch.float64), d((n,), torch.float64)),
+                "d_out": (d((self.R, n), torch.float64), d((self.R,), torch.float64), d((self.R,), torch.int32), d((self.R,), torch.int32)),
+                "h_out": (pin((self.R, n), torch.float64), pin((self.R,), torch.float64), pin((self.R,), torch.int32), pin((self.R,), torch.int32)),
+                "record": d((RECORD_HEAD + n,), torch.float64), "gathered": d((world, RECORD_HEAD + n), torch.float64),
+                "best": d((RECORD_HEAD + n,), torch.float64), "h_best": pin((RECORD_HEAD + n,), torch.float64),
+            })
+
+    def submit(self, slot, target, x0):
+        """target (8,), x0 (n,): host arrays; copied into the slot's pinned buffers, then everything is enqueued."""
+        import torch
+        s = self.slots[slot]
+        s["h_in"][0].numpy()[:] = target
+        s["h_in"][1].numpy()[:] = x0
+        with torch.cuda.stream(s["stream"]):
+            s["d_in"][0].copy_(s["h_in"][0], non_blocking=True)
+            s["d_in"][1].copy_(s["h_in"][1], non_blocking=True)
+            best, _ = ik_restart_sharded(self.robot, self.config, s["d_in"][0], s["d_in"][1], self.R, rank=self.rank,
+                                         world=self.world, group=self.group, tile=self.tile, out=s["d_out"],
+                                         record=s["record"], gathered=s["gathered"], best=s["best"])
+            for h, dv in zip(s["h_out"], s["d_out"]):
+                h.copy_(dv, non_blocking=True)
+            s["h_best"].copy_(best, non_blocking=True)
+
+    def result(self, slot):
+        """Waits for the slot's step; returns (q, f, status, evals, global_best_record) as numpy views of pinned memory."""
+        s = self.slots[slot]
+        s["stream"].synchronize()
+        return tuple(h.numpy() for h in s["h_out"]) + (s["h_best"].numpy(),)

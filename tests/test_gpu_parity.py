@@ -287,6 +287,84 @@ def test_config2_full_size_properties():
     assert np.array_equal(qb[0], q[ok][np.argmin(d)])
 
 
+def _device_targets(r, ch, T, seed):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lb, ub = torch.from_numpy(ch.lb).cuda(), torch.from_numpy(ch.ub).cuda()
+    qs = torch.rand((T, ch.n), dtype=torch.float64, device="cuda", generator=g) * (ub - lb) + lb
+    x0 = (torch.rand((T, ch.n), dtype=torch.float64, device="cuda", generator=g) * (ub - lb) + lb).contiguous()
+    return r.eval_batch(qs, want=("ee",))["ee"].contiguous(), x0, lb, ub
+
+
+def test_config3_full_size_properties():
+    """UR5, 1 Mi independent reachable targets, Speed, <= 32 restarts (BASELINE config 3): every target reported solved
+    re-evaluates below tol_f inside the limits; the winner is the LOWEST converged restart index (= the reference with
+    one thread, lib.rs:409-412) on a sample checked against the twin; per-target success ~ 1."""
+    import torch
+    r, ch = robot_and_chain("ur5")
+    T, R = 1 << 20, 32
+    tg, x0, lb, ub = _device_targets(r, ch, T, 42)
+    cfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R)
+    q, f, st, extra = r.ik_batch(cfg, tg, x0, restarts=R, stats=True)
+    ok = torch.as_tensor(cfg.is_success(st.cpu().numpy()), device="cuda")
+    assert float(ok.double().mean()) > 0.9995
+    fe = r.eval_batch(q, tg, want=("f",))["f"]
+    assert bool((fe[ok] < cfg.tol_f).all()) and bool(((q[ok] >= lb) & (q[ok] <= ub)).all())
+    assert int(extra["restart"][ok].max()) < R
+    idx = torch.randperm(T, generator=torch.Generator().manual_seed(1))[:48]
+    tg_h, x0_h, q_h, rs_h = tg[idx].cpu().numpy(), x0[idx].cpu().numpy(), q[idx].cpu().numpy(), extra["restart"][idx].cpu().numpy()
+    P = O.twin_params(layout=twin_layout(ch))
+    for k in range(len(idx)):
+        ref = O.twin_ik(ch, tg_h[k], x0_h[k], 0, R, "speed", P)
+        assert ref["found"] and int(rs_h[k]) == ref["restart"] and np.array_equal(q_h[k], ref["q"])
+
+
+def test_config4_full_size_properties():
+    """20-DOF snake, 262 144 seeds to one target (BASELINE config 4, tile kernel): converged records re-evaluate below
+    tol_f inside the (tight) limits; a sample of seeds is bit-identical to the twin; pinned joints sit ON a limit."""
+    r, ch = robot_and_chain("snake20")
+    rng = np.random.default_rng(42)
+    tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+    x0 = 0.5 * (ch.lb + ch.ub)
+    R = 262144
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R)
+    ok = st == 1
+    assert ok.mean() > 0.8
+    fe = r.eval_batch(q, tgt, want=("f",))["f"]
+    assert np.all(fe[ok] < cfg.tol_f) and np.all(q >= ch.lb) and np.all(q <= ch.ub)
+    assert ((q[ok] == ch.lb) | (q[ok] == ch.ub)).any()  # the joint-limit stress really exercises the projection
+    for i in rng.choice(R, 64, replace=False):
+        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1, O.twin_params(layout=0))
+        assert tst[0] == st[i] and tev[0] == ev[i] and np.array_equal(tq[0], q[i])
+
+
+def test_config5_shard_full_size_properties():
+    """Panda, Quality, 256 restarts x 131 072 targets = one GPU's shard of BASELINE config 5: every target solved and
+    re-verified; Quality is never farther from the seed than Speed on the same targets (tests/test_ik.rs:132-182 at
+    scale); a sample equals the twin's arg-min over all 256 restarts."""
+    import torch
+    r, ch = robot_and_chain("panda")
+    T, R = 131072, 256
+    tg, x0, lb, ub = _device_targets(r, ch, T, 7)
+    qual = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    speed = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R)
+    q, f, st = r.ik_batch(qual, tg, x0, restarts=R)
+    qs, fs, ss = r.ik_batch(speed, tg, x0, restarts=R)
+    ok = torch.as_tensor(qual.is_success(st.cpu().numpy()), device="cuda")
+    oks = torch.as_tensor(speed.is_success(ss.cpu().numpy()), device="cuda")
+    assert float(ok.double().mean()) > 0.9999 and bool((ok == oks).all())
+    fe = r.eval_batch(q, tg, want=("f",))["f"]
+    assert bool((fe[ok] < qual.tol_f).all()) and bool(((q[ok] >= lb) & (q[ok] <= ub)).all())
+    dq, ds = ((q - x0) ** 2).sum(dim=1), ((qs - x0) ** 2).sum(dim=1)
+    assert bool((dq[ok] <= ds[ok]).all())
+    idx = torch.randperm(T, generator=torch.Generator().manual_seed(2))[:6]
+    P = O.twin_params(layout=twin_layout(ch))
+    for k in idx.tolist():
+        ref = O.twin_ik(ch, tg[k].cpu().numpy(), x0[k].cpu().numpy(), 0, R, "quality", P)
+        assert ref["found"] and np.array_equal(q[k].cpu().numpy(), ref["q"])
+
+
 # ------------------------------------------------------------------ best-pick records (cross-GPU exchange building blocks)
 @pytest.mark.parametrize("mode", ["speed", "quality"])
 def test_attempts_best_record_matches_reference_selection(mode):
