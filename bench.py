@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEEDS_PER_GPU = 65536
+E2E_DEPTH_MULTI = 4  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
 TOL_F = 1e-6
 METRIC = "IK solves/sec (success-gated, Panda 7-DOF)"
@@ -286,21 +287,24 @@ def run_product(args):
         for s in range(max(Ke - 2, 0), Ke):
             e2e_conv += finish(s & 1)
     else:
-        pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=2, device=dev)
-        for s in range(2):  # warm the slots (NCCL stream setup)
+        # depth 4: the NCCL kernel of step s only gets SM resources once step s+1's solve kernel drains, so a step
+        # completes about one step late; four slots keep two solve kernels in flight regardless
+        D = E2E_DEPTH_MULTI
+        pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=D, device=dev)
+        for s in range(D):  # warm the slots (NCCL stream setup)
             pipe.submit(s, tg_host[W], x0_host)
-        for s in range(2):
+        for s in range(D):
             pipe.result(s)
         dist.barrier()
         t0 = time.perf_counter()
         for s in range(Ke):
-            k = s & 1
-            if s >= 2:
+            k = s % D
+            if s >= D:
                 r_ = pipe.result(k)
                 e2e_conv += int((r_[2] == 1).sum()) * int(r_[4][0] >= 0)
             pipe.submit(k, tg_host[W + (s % K)], x0_host)
-        for s in range(max(Ke - 2, 0), Ke):
-            r_ = pipe.result(s & 1)
+        for s in range(max(Ke - D, 0), Ke):
+            r_ = pipe.result(s % D)
             e2e_conv += int((r_[2] == 1).sum()) * int(r_[4][0] >= 0)
     e2e_s = time.perf_counter() - t0
     h2d = 8 * 8 + n * 8
@@ -371,13 +375,13 @@ def run_product(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, tile or 1),
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": 2,
+                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": 2 if world == 1 else E2E_DEPTH_MULTI,
                     "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
                             "OPTIK_BATCH_ASYNC (C ABI), two streams / two buffer sets; host reads every step's records"
                             if world == 1 else
                             "optik_b200.dist.HostStepPipeline: per step H2D from pinned buffers -> optik_gpu_ik_attempts "
                             "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
-                            "the records and the global best, all on the step's stream; two steps in flight"),
+                            "the records and the global best, all on the step's stream; %d steps in flight" % E2E_DEPTH_MULTI),
                     "blocking_call_value": sync_conv / sync_s, "blocking_call_ms_median": float(np.median(sync_times) * 1e3)},
             "gpu_launches": (3 if world == 1 else 4) * K,  # per step: solve_t1 + select (slice pass + final pass) [+ select_records]
             "roofline": roof,

@@ -642,3 +642,23 @@ def test_diff_ik_edge_cases():
     snake, _ = robot_and_chain("snake20")
     with pytest.raises(ob.OptikError):
         snake.diff_ik_batch(np.zeros((1, 20)), np.zeros(6), np.ones(20))
+
+
+@pytest.mark.parametrize("name", ["ur3e", "panda"])
+def test_cpp_consumer_end_to_end(name, tmp_path):
+    """examples/example.cpp:19-42 protocol through a C++ wrapper that binds the reference's own FFI declarations
+    (tests/cpp_wrapper_probe.cpp): default SolverConfig (Speed, max_time 0.1 s, unlimited restarts), random seed ->
+    FK-generated target; every returned solution reproduces the target pose inside the limits."""
+    import os, re, subprocess
+    from conftest import ROOT
+    exe = tmp_path / "cpp_wrapper_probe"
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cpp_wrapper_probe.cpp"),
+                           "-o", str(exe), ob.LIB_PATH, "-Wl,-rpath," + os.path.dirname(ob.LIB_PATH)])
+    base, ee = ob.ROBOT_LINKS[name]
+    p = subprocess.run([str(exe), ob.data_path(name), base, ee, "gpu", "200"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    m = re.search(r"solved=(\d+)/200 accurate=(\d+) diff_ik_ok=(\d+) jac=(\d+)", p.stdout)
+    assert m, p.stdout
+    solved, accurate, dik, jac = map(int, m.groups())
+    assert solved >= 198 and accurate == solved and jac == 6 * (6 if name == "ur3e" else 7)
+    assert dik >= solved - 2  # a solution may sit at a singular pose (diff_ik -> None)

@@ -173,3 +173,14 @@ def test_header_is_valid_c_and_links(tmp_path):
     assert "EE link 'nope' does not exist" in p.stdout
     # the ctypes mirror of optik_gpu_batch_opts has the C compiler's layout
     assert f"sizeof(optik_gpu_batch_opts)={C.sizeof(ob._BatchOpts)}" in p.stdout
+
+
+def test_cpp_consumer_with_its_own_declarations_links_and_runs(tmp_path):
+    """A C++ wrapper that declares the 11 symbols ITSELF against its own opaque robot type and SolverConfig POD, the way
+    crates/optik-cpp/src/lib.cpp:5-31 does, links against liboptik_b200.so and drives the non-compute calls."""
+    exe = tmp_path / "cpp_wrapper_probe"
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", os.path.join(ROOT, "tests", "cpp_wrapper_probe.cpp"),
+                           "-o", str(exe), ob.LIB_PATH, "-Wl,-rpath," + os.path.dirname(ob.LIB_PATH)])
+    base, ee = ob.ROBOT_LINKS["ur3e"]
+    p = subprocess.run([str(exe), ob.data_path("ur3e"), base, ee, "cpu"], capture_output=True, text=True)
+    assert p.returncode == 0 and "n=6 inside=1" in p.stdout, p.stdout + p.stderr
