@@ -157,6 +157,14 @@ typedef struct optik_gpu_batch_opts {
  * (optik_host_alloc), otherwise the copies are staged synchronously.  Two streams with two sets of buffers overlap
  * one call's transfers with the next call's kernels.  opts->counters is then SET (not incremented). */
 #define OPTIK_BATCH_ASYNC 1u
+/* Speed-mode optik_gpu_ik_batch in PHASES: restarts [0,2) of every target in one launch, then the still-unsolved
+ * targets are compacted on the device and only they run further restarts (in order while they fill the GPU, in
+ * parallel chunks with early exit afterwards).  Same per-target result (lowest-index converged restart, lib.rs:409-412),
+ * no geometric tail of unlucky targets: 1.3-2x the throughput of one launch.  Each phase boundary synchronises the
+ * stream to size the next launch, so DEVICE-memory calls (documented as asynchronous) only do this when asked with
+ * OPTIK_BATCH_PHASED; blocking HOST-memory calls always do, unless OPTIK_BATCH_SINGLE_LAUNCH is set. */
+#define OPTIK_BATCH_PHASED 2u
+#define OPTIK_BATCH_SINGLE_LAUNCH 4u
 
 #define OPTIK_RECORD_HEAD 8
 

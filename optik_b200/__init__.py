@@ -43,7 +43,7 @@ class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
                 ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
-BATCH_ASYNC = 1  # == OPTIK_BATCH_ASYNC
+BATCH_ASYNC, BATCH_PHASED, BATCH_SINGLE_LAUNCH = 1, 2, 4  # == OPTIK_BATCH_*
 
 
 RECORD_HEAD = 8  # candidate record: [found, score, restart, cost, status, 0, 0, 0, q...]
@@ -429,7 +429,7 @@ class Robot:
         return o, keep
 
     def ik_batch(self, config, targets, x0, restarts=None, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0,
-                 ee_offset=None, stats=False, out=None, stream=None, wait=True):
+                 ee_offset=None, stats=False, out=None, stream=None, wait=True, phased=None):
         """Robot::ik over T (target, x0) pairs in one launch.
 
         targets: (T, 8) pose8 rows {qx,qy,qz,qw,tx,ty,tz,0};  x0: (T, n).
@@ -437,6 +437,9 @@ class Robot:
         torch CUDA tensors in -> device path on torch's current stream, returns torch tensors (no sync).
         Host path with stream=<Stream> and wait=False: returns as soon as everything is enqueued; the outputs (give
         pinned `out` buffers, see pinned_empty) are valid after stream.synchronize().
+        phased: Speed-mode batches in phases (OPTIK_BATCH_PHASED: unsolved targets are compacted between launches --
+        same results, no tail of unlucky targets, but one stream sync per phase).  Default: on for blocking host
+        calls, off for device-tensor calls (which stay fully asynchronous); True / False force it.
         """
         lib = load_library()
         c = config._c()
@@ -456,6 +459,8 @@ class Robot:
             else:
                 q, f, st = out
             o, keep = self._opts(1, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
+            if phased:
+                o.flags |= BATCH_PHASED
             extra = {}
             if stats:
                 extra["restart"] = torch.empty((T,), dtype=torch.int64, device=dev)
@@ -481,6 +486,8 @@ class Robot:
             if sh is None:
                 raise ValueError("wait=False needs a stream")
             o.flags |= BATCH_ASYNC
+        if phased is False:
+            o.flags |= BATCH_SINGLE_LAUNCH
         extra = {}
         if stats:
             extra["restart"] = np.zeros(T, dtype=np.uint64)

@@ -30,6 +30,8 @@ extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n, int cols);
+extern "C" int optik_launch_compact_unsolved(const int* status, unsigned long long T, double tol_f, double tol_df_user,
+                                             double tol_dx, unsigned* list, unsigned* count, void* stream);
 extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stream);
 extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
@@ -295,17 +297,21 @@ bool config_valid(const optik_solver_config* c) {
 int solve_device(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
                  const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
                  double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
-                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
+                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr,
+                 const unsigned* d_tlist = nullptr, uint64_t chunks_override = 0) {
+  // d_tlist != null: a later phase of a phased batch -- the T targets of this launch are rows d_tlist[t] of
+  // d_targets / d_x0 and of every output; only converged winners replace what earlier phases recorded
   const int tile = choose_tile(r->n, o ? o->tile : 0, true);
   if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (num_positions <= 8), 8, 16 or 32 and >= num_positions");
   SolveParams P{};
   fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
   P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
+  P.tlist = d_tlist;
   P.max_ns = max_ns;
   P.counters = (unsigned long long*)d_counters;
   // chunks per target
   Plan plan0 = make_plan(r, tile, o ? o->blocks : 0, ~0ull);
-  uint64_t C = o ? o->chunks : 0;
+  uint64_t C = chunks_override ? chunks_override : (o ? o->chunks : 0);
   if (per_attempt_records) C = R;
   if (C == 0) {
     const uint64_t want = 2ull * (uint64_t)plan0.resident_tiles;
@@ -320,7 +326,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
   Plan plan = make_plan(r, tile, o ? o->blocks : 0, njobs);
   const int n = r->n;
-  const bool direct = (C == 1) || per_attempt_records;  // candidate records ARE the outputs
+  const bool direct = ((C == 1) || per_attempt_records) && !d_tlist;  // candidate records ARE the outputs
   // scratch: optional outputs the caller did not ask for + candidate arrays when a selection pass follows
   size_t bytes = 0;
   auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
@@ -373,10 +379,85 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     S.q_out = d_q; S.f_out = d_f; S.status_out = d_status;
     S.restart_out = (unsigned long long*)d_restart;  // optional
     S.evals_out = d_evals;                            // optional
+    if (d_tlist) { S.tlist = d_tlist; S.only_success = 1; S.add_evals = 1; }
     CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
   }
   CUDA_TRY(cudaFreeAsync(scratch, s));
   return OPTIK_OK;
+}
+
+// Speed-mode batches in PHASES.  One launch with every target's restarts in sequence ends with the few targets that
+// need 10-25 attempts (a geometric tail), and spreading restarts over parallel chunks from the start wastes attempts
+// on targets whose first seed converges.  Phase 0 runs restarts [0, K0) of every target in order; each later phase
+// compacts the still-unsolved targets on the device, reads their count (the one host sync per phase: it sizes the
+// next launch) and runs their next restarts -- in order while they still fill the GPU, one attempt per parallel chunk
+// with the `found` early exit (lib.rs:382-384) once they do not.  Per target the result is unchanged: the
+// lowest-index converged restart (lib.rs:409-412).
+// Plan (swept on B200, tools/gpu_phase_sweep.sh): 3 restarts in order per phase while the unsolved targets fill the GPU
+// twice over; afterwards ONE attempt per chunk and as many chunks per target as fill it twice (no chains at all).
+// Panda, 32 restarts: 65 536 targets 3.05 -> 1.51 ms, 262 144 targets 5.28 -> 3.56 ms, 1 Mi targets 10.9 -> 10.5 ms.
+constexpr uint64_t PHASE_K0 = 3, PHASE_K = 3, PHASE_FILL = 2;
+
+bool phased_applies(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o, uint64_t T, uint64_t R,
+                    bool per_attempt_records) {
+  if (cfg->solution_mode != OPTIK_MODE_SPEED || per_attempt_records || (o && o->chunks) || R <= PHASE_K0) return false;
+  if (T > 0xffffffffull) return false;
+  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
+  if (!tile) return false;
+  return T * 4 >= (uint64_t)make_plan(r, tile, 0, ~0ull).resident_tiles;
+}
+
+int solve_device_phased(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
+                        const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
+                        double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
+                        unsigned long long max_ns, cudaStream_t s) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
+  const uint64_t resident = (uint64_t)make_plan(r, tile, 0, ~0ull).resident_tiles;
+  // the evaluation count is needed across phases even when the caller does not ask for it
+  char* aux = nullptr;
+  const size_t aux_bytes = ((T * 4 + 255) & ~size_t(255)) + 256 + (d_evals ? 0 : ((T * 4 + 255) & ~size_t(255)));
+  CUDA_TRY(cudaMallocAsync((void**)&aux, aux_bytes, s));
+  unsigned* d_list = (unsigned*)aux;
+  unsigned* d_count = (unsigned*)(aux + ((T * 4 + 255) & ~size_t(255)));
+  int32_t* evals = d_evals ? d_evals : (int32_t*)(aux + ((T * 4 + 255) & ~size_t(255)) + 256);
+  auto remaining_ns = [&]() -> long long {  // max_time bounds the whole call (lib.rs:260-264)
+    if (!max_ns) return 0;
+    const long long used = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
+    return (long long)max_ns - used;
+  };
+  int rc = solve_device(r, cfg, o, d_targets, d_x0, T, r_begin, PHASE_K0, d_q, d_f, d_status, d_restart, evals, d_counters,
+                        max_ns, false, s, nullptr, nullptr, 1);  // one chunk: restarts strictly in order, nothing speculative
+  uint64_t done = PHASE_K0;
+  while (!rc && done < R) {
+    if (cudaMemsetAsync(d_count, 0, sizeof(unsigned), s) != cudaSuccess) { rc = fail(OPTIK_ERR_CUDA, "cudaMemsetAsync failed"); break; }
+    rc = optik_launch_compact_unsolved(d_status, T, cfg->tol_f, cfg->tol_df, cfg->tol_dx, d_list, d_count, s);
+    if (rc) { rc = fail(OPTIK_ERR_CUDA, "compact_unsolved launch failed"); break; }
+    unsigned count = 0;
+    if (cudaMemcpyAsync(&count, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(OPTIK_ERR_CUDA, "phase count readback failed"); break; }
+    if (count == 0) break;
+    unsigned long long ns = 0;
+    if (max_ns) {
+      const long long left = remaining_ns();
+      if (left <= 0) break;
+      ns = (unsigned long long)left;
+    }
+    // while the unsolved targets still fill the GPU twice over: a few more restarts each, in order; afterwards all
+    // remaining restarts, spread over parallel chunks by solve_device's own rule
+    uint64_t k, chunks;
+    if (count >= PHASE_FILL * resident && R - done > PHASE_K) { k = PHASE_K; chunks = 1; }
+    else {  // one attempt per chunk, as many chunks as fill the GPU
+      chunks = (PHASE_FILL * resident + count - 1) / count;
+      if (chunks > R - done) chunks = R - done;
+      k = chunks;
+    }
+    rc = solve_device(r, cfg, o, d_targets, d_x0, count, r_begin + done, k, d_q, d_f, d_status, d_restart, evals, d_counters,
+                      ns, false, s, nullptr, d_list, chunks);
+    done += k;
+  }
+  cudaFreeAsync(aux, s);
+  return rc;
 }
 
 int check_seeds_host(const optik_robot* r, const double* x0, uint64_t T) {  // lib.rs:251-254
@@ -639,6 +720,9 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   if (memory == 1) {
     lk.unlock();
     // seeds outside the limits cannot be checked without a sync; they are clamped by the kernel (documented)
+    if (opts && (opts->flags & OPTIK_BATCH_PHASED) && phased_applies(robot, config, opts, T, R, per_attempt))
+      return solve_device_phased(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
+                                 opts->restart_out, opts->evals_out, opts->counters, max_ns, s);
     return solve_device(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
                         opts ? opts->restart_out : nullptr, per_attempt ? evals_all : (opts ? opts->evals_out : nullptr),
                         opts ? opts->counters : nullptr, max_ns, per_attempt, s, opts ? opts->best_record_out : nullptr);
@@ -658,10 +742,18 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, T * 64, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d + o_x, x0, T * n * 8, cudaMemcpyHostToDevice, s));
   if (want_cnt) CUDA_TRY(cudaMemsetAsync(d + o_c, 0, 24, s));
-  int rc = solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
-                        (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
-                        evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
-                        per_attempt, s, want_best ? (double*)(d + o_br) : nullptr);
+  // host-memory calls synchronise anyway: Speed-mode batches run in phases unless the caller enqueues only (async)
+  const bool phased = !async && !(opts && (opts->flags & OPTIK_BATCH_SINGLE_LAUNCH)) &&
+                      phased_applies(robot, config, opts, T, R, per_attempt);
+  int rc = phased
+               ? solve_device_phased(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R,
+                                     (double*)(d + o_q), (double*)(d + o_f), (int32_t*)(d + o_s),
+                                     want_rs ? (uint64_t*)(d + o_r) : nullptr, evals_host ? (int32_t*)(d + o_e) : nullptr,
+                                     want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns, s)
+               : solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
+                              (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
+                              evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
+                              per_attempt, s, want_best ? (double*)(d + o_br) : nullptr);
   if (rc) { cudaFreeAsync(d, s); return rc; }
   CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
   unsigned long long job = 0;
   // lanes of this tile (shuffles inside the divergent transition code name exactly the tile's lanes)
   const unsigned tile_mask = (TILE == 32) ? 0xffffffffu : (((1u << (TILE & 31)) - 1u) << (((threadIdx.x & 31) / TILE) * TILE));
-  unsigned long long tgt_id = 0, r_idx = 0;
+  unsigned long long tgt_id = 0, src_id = 0, r_idx = 0;
   bool need_job = true, running = false, done = false, best_has = false, rec_any = false;
   se3 O;                          // lane: this lane's origin (lane 0: pre-multiplied by T_tgt^-1 per job)
   O.q = J.oq; O.t = J.ot;
@@ -203,10 +203,11 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
           job = __shfl_sync(tile_mask, next, 0, TILE);
           if (job >= njobs) { done = true; break; }
           tgt_id = job / P.C;
+          src_id = P.tlist ? (unsigned long long)P.tlist[tgt_id] : tgt_id;  // row of targets / x0 (phased batches)
           r_idx = P.r_begin + job % P.C;
-          x0 = (lane < n) ? P.x0[tgt_id * n + lane] : 0.0;
+          x0 = (lane < n) ? P.x0[src_id * n + lane] : 0.0;
           if (lane == 0) {  // FK in the target's frame: O_0 <- T_tgt^-1 * origin_0
-            const se3 tgt = load_pose8(P.targets + 8 * tgt_id);
+            const se3 tgt = load_pose8(P.targets + 8 * src_id);
             se3 ti;
             ti.q = qconj(tgt.q);
             ti.t = neg3(qrot(ti.q, tgt.t));
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
 
     // ---------------- evaluate the trial point (every lane of the warp, uniform instruction stream)
     double ft, rt[6], Jt[6];
-    evaluate<TILE>(J, O, s_tip, P.targets + 8 * tgt_id, P.wl, P.wa, P.weighted, P.has_prismatic, n, lane, qt_, ft, rt, Jt);
+    evaluate<TILE>(J, O, s_tip, P.targets + 8 * src_id, P.wl, P.wa, P.weighted, P.has_prismatic, n, lane, qt_, ft, rt, Jt);
 
     // ---------------- bookkeeping (mirrors NLopt's stop tests as the reference configures them, lib.rs:345-347)
     int status = OPTIK_ST_NONE;
@@ -403,10 +404,14 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     return;
   }
   const unsigned long long win = w.idx;
-  if (P.q_out)
-    for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[t * P.n + j] = P.cand_q[win * P.n + j];
+  // phased batches: results are scattered to the target's row, only a converged winner replaces the record the
+  // earlier phases left there, evaluations add up
+  const unsigned long long ot = P.tlist ? (unsigned long long)P.tlist[t] : t;
+  const bool write = !P.only_success || w.has > 0;
+  if (P.q_out && write)
+    for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[ot * P.n + j] = P.cand_q[win * P.n + j];
   if (P.record_out) {
-    double* rec = P.record_out + t * (8 + P.n);
+    double* rec = P.record_out + ot * (8 + P.n);
     for (int j = threadIdx.x; j < P.n; j += blockDim.x) rec[8 + j] = P.cand_q[win * P.n + j];
     if (threadIdx.x == 0) {
       const unsigned long long rr = P.cand_restart[win];
@@ -419,11 +424,50 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     }
   }
   if (threadIdx.x == 0 && P.f_out) {
-    P.f_out[t] = P.cand_f[win];
-    if (P.restart_out) P.restart_out[t] = P.cand_restart[win];
-    P.status_out[t] = P.cand_status[win];
-    if (P.evals_out) P.evals_out[t] = w.evals;
+    if (write) {
+      P.f_out[ot] = P.cand_f[win];
+      if (P.restart_out) P.restart_out[ot] = P.cand_restart[win];
+      P.status_out[ot] = P.cand_status[win];
+    }
+    if (P.evals_out) P.evals_out[ot] = (P.add_evals ? P.evals_out[ot] : 0) + w.evals;
   }
+}
+
+// Phased batches with ONE chunk per target: the candidate record of job t goes to row tlist[t] if it converged;
+// evaluations add up.  (select_kernel spends a 256-thread block per target, which is wasteful for a single candidate.)
+__global__ void scatter_kernel(const __grid_constant__ SelectParams P) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.T) return;
+  const unsigned long long ot = P.tlist ? (unsigned long long)P.tlist[t] : t;
+  const int st = P.cand_status[t];
+  const bool has = (P.tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (P.tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
+                   (P.tol_dx >= 0.0 && st == OPTIK_ST_XTOL);
+  if (!P.only_success || has) {
+    for (int j = 0; j < P.n; j++) P.q_out[ot * P.n + j] = P.cand_q[t * P.n + j];
+    P.f_out[ot] = P.cand_f[t];
+    if (P.restart_out) P.restart_out[ot] = P.cand_restart[t];
+    P.status_out[ot] = st;
+  }
+  if (P.evals_out) P.evals_out[ot] = (P.add_evals ? P.evals_out[ot] : 0) + P.cand_evals[t];
+}
+
+// Phased Speed-mode batches: indices of the targets whose recorded status is not a success (unordered)
+__global__ void compact_unsolved_kernel(const int* __restrict__ status, unsigned long long T, double tol_f, double tol_df_user,
+                                        double tol_dx, unsigned* __restrict__ list, unsigned* __restrict__ count) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool unsolved = false;
+  if (t < T) {
+    const int st = status[t];
+    unsolved = !((tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
+                 (tol_dx >= 0.0 && st == OPTIK_ST_XTOL));
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, unsolved);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (lane == (__ffs(m) - 1)) base = atomicAdd(count, (unsigned)__popc(m));  // one atomic per warp
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (unsolved) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)t;
 }
 
 }  // namespace optik
@@ -467,11 +511,21 @@ extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, vo
   }
   return (int)cudaGetLastError();
 }
+extern "C" int optik_launch_compact_unsolved(const int* status, unsigned long long T, double tol_f, double tol_df_user,
+                                             double tol_dx, unsigned* list, unsigned* count, void* stream) {
+  const unsigned blocks = (unsigned)((T + 255) / 256);
+  optik::compact_unsolved_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(status, T, tol_f, tol_df_user, tol_dx, list, count);
+  return (int)cudaGetLastError();
+}
 extern "C" int optik_select_partial_bytes(void) { return (int)sizeof(optik::SelKey); }
 // slices == 1: one launch.  slices > 1: caller provides partial scratch (T*slices*optik_select_partial_bytes()).
 extern "C" int optik_launch_select(const SelectParams* p, unsigned slices, void* partial_scratch, void* stream) {
   SelectParams P = *p;
   P.final_pass = 0; P.partials = 0; P.partial = nullptr; P.partial_out = nullptr;
+  if (P.C == 1 && P.tlist && !P.record_out) {  // one candidate per target: a plain scatter
+    optik::scatter_kernel<<<(unsigned)((P.T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+    return (int)cudaGetLastError();
+  }
   if (slices <= 1) {
     optik::select_kernel<<<dim3((unsigned)P.T, 1), 256, 0, (cudaStream_t)stream>>>(P);
     return (int)cudaGetLastError();

@@ -33,7 +33,7 @@ DEV void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
   uint32_t x[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) x[i] = s[i];
-#pragma unroll
+#pragma unroll 1  // rolled: the block is drawn once per attempt, its code should not crowd the evaluation loop out of the instruction cache
   for (int r = 0; r < 4; r++) {
     OPTIK_QR(x[0], x[4], x[8], x[12]) OPTIK_QR(x[1], x[5], x[9], x[13])
     OPTIK_QR(x[2], x[6], x[10], x[14]) OPTIK_QR(x[3], x[7], x[11], x[15])
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
   const bool prefetch = njobs >= 8ull * T1_THREADS * gridDim.x;
 
   // ---- per-thread state.  A "job" is one (target, chunk): restarts r_begin+c, +C, ... run in index order.
-  unsigned long long job = 0, tgt_id = 0, r_idx = 0, nxt_job = 0, nxt_r = 0;
+  unsigned long long job = 0, tgt_id = 0, src_id = 0, r_idx = 0, nxt_job = 0, nxt_r = 0;
   bool running = false, job_open = false, best_has = false, rec_any = false, have_next = false, queue_done = false, done = false;
   se3 O0;  // origin of joint 0 pre-multiplied by T_tgt^-1 (FK in the target's frame)
   O0.q.x = O0.q.y = O0.q.z = 0; O0.q.w = 1; O0.t = mk3(0, 0, 0);
@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
             got = nxt_r < P.r_end;
             if (!got) {  // chunk without any restart (C > R): empty record, job consumed
               const unsigned long long t = (P.C == 1) ? nxt_job : (P.T == 1 ? 0ull : nxt_job / P.C);
-              for (int j = 0; j < n; j++) P.cand_q[nxt_job * n + j] = P.x0[t * n + j];
+              const unsigned long long ts = P.tlist ? (unsigned long long)P.tlist[t] : t;
+              for (int j = 0; j < n; j++) P.cand_q[nxt_job * n + j] = P.x0[ts * n + j];
               P.cand_f[nxt_job] = 0.0; P.cand_score[nxt_job] = 0.0; P.cand_restart[nxt_job] = nxt_r;
               P.cand_status[nxt_job] = OPTIK_ST_SKIPPED; P.cand_evals[nxt_job] = 0;
             }
@@ -137,9 +138,10 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
               }
           } else {
             const unsigned long long t = (P.C == 1) ? nxt_job : (P.T == 1 ? 0ull : nxt_job / P.C);
+            const unsigned long long ts = P.tlist ? (unsigned long long)P.tlist[t] : t;
             for (int j = 0; j < n; j++) {
               const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-              qn[j * T1_THREADS] = fmin(fmax(P.x0[t * n + j], jc[12]), jc[13]);
+              qn[j * T1_THREADS] = fmin(fmax(P.x0[ts * n + j], jc[12]), jc[13]);
             }
           }
           have_next = true;
@@ -154,7 +156,8 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
           if (job_open) P.cand_evals[job] = job_evals;
           job = nxt_job;
           tgt_id = (P.C == 1) ? job : (P.T == 1 ? 0ull : job / P.C);
-          const se3 tgt = load_pose8(P.targets + 8 * tgt_id);
+          src_id = P.tlist ? (unsigned long long)P.tlist[tgt_id] : tgt_id;  // row of targets / x0 (phased batches)
+          const se3 tgt = load_pose8(P.targets + 8 * src_id);
           se3 ti, o0;
           ti.q = qconj(tgt.q);
           ti.t = neg3(qrot(ti.q, tgt.t));
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
           a0.x = s_chain[8]; a0.y = s_chain[9]; a0.z = s_chain[10]; a0.w = 0.0;
           O0a = qmul(O0.q, a0);
           best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
-          for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[tgt_id * n + j];  // record if no attempt runs
+          for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[src_id * n + j];  // record if no attempt runs
           P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = nxt_r;
           P.cand_status[job] = OPTIK_ST_SKIPPED;
           job_open = true;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     v3 rl = elin, ra = ec.w;
     qt tq;
     if (P.weighted) {
-      const double* tp = P.targets + 8 * tgt_id;
+      const double* tp = P.targets + 8 * src_id;
       tq.x = tp[0]; tq.y = tp[1]; tq.z = tp[2]; tq.w = tp[3];
       rl = weight3(tq, P.wl, elin); ra = weight3(tq, P.wa, ec.w);
     }
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
       double score = 0.0;
       if (success && !speed)  // Quality score ||q - x0||^2 (lib.rs:402-407)
         for (int j = 0; j < n; j++) {
-          const double d = qt_[j * T1_THREADS] - P.x0[tgt_id * n + j];
+          const double d = qt_[j * T1_THREADS] - P.x0[src_id * n + j];
           score = fma(d, d, score);
         }
       n_attempts++; n_evals += evals; job_evals += evals;

@@ -69,6 +69,7 @@ struct SolveParams {
   int* cand_status;                   // status of the recorded attempt
   int* cand_evals;                    // evaluations spent by this chunk (all its attempts)
   unsigned long long* counters;       // [0] attempts run, [1] evaluations, [2] converged attempts (optional)
+  const unsigned* tlist;              // phased batches: target t of THIS launch reads row tlist[t] of targets / x0 (or null)
 };
 
 namespace optik { struct SelKey; }
@@ -90,6 +91,9 @@ struct SelectParams {
   int* evals_out;                    // [T] total evaluations spent on the target
   double* record_out;                // [T][8+n] packed candidate record (see optik_b200.h), may be null
   int mode;                          // 1 Quality, 2 Speed (record score)
+  // phased batches: scatter outputs to row tlist[t]; write only converged winners; add to evals_out instead of setting it
+  const unsigned* tlist;
+  int only_success, add_evals;
   // two-level reduction for targets with very many chunks (set by optik_launch_select)
   int final_pass;
   unsigned partials;

@@ -662,3 +662,33 @@ def test_cpp_consumer_end_to_end(name, tmp_path):
     solved, accurate, dik, jac = map(int, m.groups())
     assert solved >= 198 and accurate == solved and jac == 6 * (6 if name == "ur3e" else 7)
     assert dik >= solved - 2  # a solution may sit at a singular pose (diff_ik -> None)
+
+
+@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8)])
+def test_phased_speed_batches_equal_single_launch(name, T, R):
+    """OPTIK_BATCH_PHASED only reschedules the restarts: q, cost, status, winning restart and the per-target success set
+    are identical to the single-launch result, on the host path (phased by default) and on the device path (on
+    request); evaluations are not compared (a single launch with parallel chunks runs speculative attempts)."""
+    import torch
+    r, ch = robot_and_chain(name)
+    tg, x0, lb, ub = _device_targets(r, ch, T, 11)
+    cfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R)
+    q1, f1, s1, e1 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True)                  # device path, one launch
+    q2, f2, s2, e2 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True, phased=True)     # device path, phased
+    ok = torch.as_tensor(cfg.is_success(s1.cpu().numpy()), device="cuda")
+    assert torch.equal(s1, s2) and torch.equal(q1[ok], q2[ok]) and torch.equal(f1[ok], f2[ok])
+    assert torch.equal(e1["restart"][ok], e2["restart"][ok])
+    q3, f3, s3, e3 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, stats=True)  # host path: phased
+    q4, f4, s4 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, phased=False)
+    okh = ok.cpu().numpy()
+    assert np.array_equal(s3, s1.cpu().numpy()) and np.array_equal(q3[okh], q1[ok].cpu().numpy())
+    assert np.array_equal(e3["restart"][okh], e1["restart"][ok].cpu().numpy().astype(np.uint64))
+    assert np.array_equal(s4, s3) and np.array_equal(q4[okh], q3[okh])
+    # the lowest-index rule against the twin on a sample
+    P = O.twin_params(layout=twin_layout(ch))
+    tg_h, x0_h = tg.cpu().numpy(), x0.cpu().numpy()
+    for t in range(0, T, T // 24):
+        ref = O.twin_ik(ch, tg_h[t], x0_h[t], 0, R, "speed", P)
+        assert ref["found"] == bool(okh[t])
+        if ref["found"]:
+            assert int(e3["restart"][t]) == ref["restart"] and np.array_equal(q3[t], ref["q"])
