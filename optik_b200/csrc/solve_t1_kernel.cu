@@ -104,11 +104,15 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     // ---------------- seed pipeline.  Drawing a restart seed (one ChaCha8 block, ~800 integer instructions) by a lone
     // lane would cost a full warp issue slot per instruction, so seeds are PREFETCHED: whenever some lane is idle
     // without a prefetched attempt, every lane lacking one refills in the same pass (lib.rs:360-370 per lane).
-    // With few jobs per thread (prefetch == 0) only idle lanes refill, so that no lane hoards a job another could run.
+    // With few jobs per thread (prefetch == 0) only idle lanes pull from the QUEUE, so that no lane hoards a job another
+    // could run.
     if (__any_sync(FULL, !running && !have_next && !queue_done)) {
-      if (!have_next && !queue_done && (prefetch || !running)) {
+      // the next restart of a thread's OWN chunk can always be drawn ahead (nobody else could run it); only pulling
+      // a new job off the queue early is restricted to launches with many jobs per thread
+      const bool own_next = job_open && r_idx + P.C < P.r_end;
+      if (!have_next && !queue_done && (prefetch || !running || own_next)) {
         bool got = false;
-        if (job_open && r_idx + P.C < P.r_end) {  // next restart of my own chunk
+        if (own_next) {  // next restart of my own chunk
           nxt_job = job; nxt_r = r_idx + P.C; got = true;
         } else {
           nxt_job = atomicAdd(P.queue, 1ull);  // dynamic job queue

@@ -39,4 +39,6 @@ for ph in (False, True):
     run("panda", 1 << 16, 32, phased=ph)
     run("panda", 1 << 14, 32, phased=ph)
 run("panda", 1 << 20, 32, mode="quality")
+run("panda", 1 << 18, 32, mode="quality")
+run("panda", 1 << 16, 256, mode="quality")
 run("panda", 1 << 20, 1)

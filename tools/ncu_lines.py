@@ -27,6 +27,7 @@ def main():
     ap.add_argument("report")
     ap.add_argument("cu")
     ap.add_argument("--kernel-regex", default=None, help="select the ncu result whose kernel name matches")
+    ap.add_argument("--index", type=int, default=0, help="which captured launch of the report (0 = first)")
     ap.add_argument("--min", type=float, default=0.4, help="print lines with at least this %% of instructions or samples")
     ap.add_argument("--so", default=os.path.join(ROOT, "optik_b200", "lib", "liboptik_b200.so"))
     a = ap.parse_args()
@@ -41,8 +42,8 @@ def main():
     if a.kernel_regex:
         cmd += ["-k", "regex:" + a.kernel_regex]
     rows = list(csv.reader(io.StringIO(subprocess.run(cmd, capture_output=True, text=True, check=True).stdout)))
-    # first result only
-    start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    start = starts[a.index]
     hdr = rows[start]
     data = []
     for r in rows[start + 1:]:
