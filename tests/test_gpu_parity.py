@@ -692,3 +692,27 @@ def test_phased_speed_batches_equal_single_launch(name, T, R):
         assert ref["found"] == bool(okh[t])
         if ref["found"]:
             assert int(e3["restart"][t]) == ref["restart"] and np.array_equal(q3[t], ref["q"])
+
+
+@pytest.mark.parametrize("name", ["panda", "ur5"])
+def test_evaluator_unaligned_and_ragged_device_inputs(name):
+    """The evaluator's TMA tile loads need 16-byte aligned joint vectors and full 32-configuration tiles; a device
+    tensor sliced at an odd row (8-byte aligned only) and ragged batch sizes take the plain-load path -- same bits."""
+    import torch
+    r, ch = robot_and_chain(name)
+    B = 4 * 148 * 128 + 77  # more than one tile per warp of the persistent grid, ragged end
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lb, ub = torch.from_numpy(ch.lb).cuda(), torch.from_numpy(ch.ub).cuda()
+    q = (torch.rand((B + 1, ch.n), dtype=torch.float64, device="cuda", generator=g) * (ub - lb) + lb).contiguous()
+    tg = r.eval_batch(q, want=("ee",))["ee"].contiguous()
+    full = r.eval_batch(q, tg)
+    part = r.eval_batch(q[1:], tg[1:])  # q[1:] starts 8*n bytes in: unaligned for odd n
+    assert (q[1:].data_ptr() % 16 != 0) == (ch.n % 2 == 1)
+    for k in ("ee", "jac", "f", "grad"):
+        assert torch.equal(full[k][1:], part[k]), k
+    fk_only = r.eval_batch(q[1:], want=("ee",))["ee"]  # the double-buffered FK-only variant
+    assert torch.equal(fk_only, part["ee"])
+    for b in (1, 31, 32, 33, 127, 129):
+        small = r.eval_batch(q[:b].contiguous(), tg[:b].contiguous())
+        for k in ("ee", "jac", "f", "grad"):
+            assert torch.equal(small[k], full[k][:b]), (k, b)
