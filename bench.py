@@ -243,7 +243,7 @@ def run_product(args):
     tg_host[:] = targets.cpu().numpy()
     x0_host = ob.pinned_empty(n)
     x0_host[:] = 0.5 * (lb + ub)
-    Ke = min(K, 200)
+    Ke = min(K, int(os.environ.get("OPTIK_BENCH_E2E_STEPS", "200")))
     sets = [((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
              ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)) for _ in range(2)]
 
