@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEEDS_PER_GPU = 65536
+E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "2"))  # host-buffer calls in flight on one GPU
 E2E_DEPTH_MULTI = 4  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
 TOL_F = 1e-6
@@ -245,7 +246,7 @@ def run_product(args):
     x0_host[:] = 0.5 * (lb + ub)
     Ke = min(K, int(os.environ.get("OPTIK_BENCH_E2E_STEPS", "200")))
     sets = [((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
-             ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)) for _ in range(2)]
+             ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)) for _ in range(E2E_DEPTH_SINGLE)]
 
     def finish(k):
         """host side of a step: wait for its stream, read the result (count converged records; cross-GPU best-pick)"""
@@ -278,14 +279,14 @@ def run_product(args):
     if world == 1:
         t0 = time.perf_counter()
         for s in range(Ke):
-            k = s & 1
-            if s >= 2:
+            k = s % E2E_DEPTH_SINGLE
+            if s >= E2E_DEPTH_SINGLE:
                 e2e_conv += finish(k)
             hrec, hrecord, stream = sets[k]
             robot.ik_attempts(cfg, tg_host[W + (s % K)], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
                               record=hrecord, stream=stream, wait=False)
-        for s in range(max(Ke - 2, 0), Ke):
-            e2e_conv += finish(s & 1)
+        for s in range(max(Ke - E2E_DEPTH_SINGLE, 0), Ke):
+            e2e_conv += finish(s % E2E_DEPTH_SINGLE)
     else:
         # depth 4: the NCCL kernel of step s only gets SM resources once step s+1's solve kernel drains, so a step
         # completes about one step late; four slots keep two solve kernels in flight regardless
@@ -375,9 +376,9 @@ def run_product(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, tile or 1),
             "clocks": clocks,
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": 2 if world == 1 else E2E_DEPTH_MULTI,
+                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3, "pipeline_depth": E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI,
                     "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
-                            "OPTIK_BATCH_ASYNC (C ABI), two streams / two buffer sets; host reads every step's records"
+                            "OPTIK_BATCH_ASYNC (C ABI), one stream + buffer set per call in flight; host reads every step's records"
                             if world == 1 else
                             "optik_b200.dist.HostStepPipeline: per step H2D from pinned buffers -> optik_gpu_ik_attempts "
                             "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
