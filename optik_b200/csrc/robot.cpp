@@ -393,7 +393,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
 // next launch) and runs their next restarts -- in order while they still fill the GPU, one attempt per parallel chunk
 // with the `found` early exit (lib.rs:382-384) once they do not.  Per target the result is unchanged: the
 // lowest-index converged restart (lib.rs:409-412).
-// Plan (swept on B200, tools/gpu_phase_sweep.sh): 3 restarts in order per phase while the unsolved targets fill the GPU
+// Plan (swept on B200 over K0, K, fill factor and one-attempt-per-chunk vs chained chunks): 3 restarts in order per phase while the unsolved targets fill the GPU
 // twice over; afterwards ONE attempt per chunk and as many chunks per target as fill it twice (no chains at all).
 // Panda, 32 restarts: 65 536 targets 3.05 -> 1.51 ms, 262 144 targets 5.28 -> 3.56 ms, 1 Mi targets 10.9 -> 10.5 ms.
 constexpr uint64_t PHASE_K0 = 3, PHASE_K = 3, PHASE_FILL = 2;
