@@ -72,6 +72,39 @@ DEV void task_col(const ErrCoef& c, v3 lin, v3 ang, v3& top, v3& bot) {
   bot = ja;
 }
 
+// Thread-per-seed layout: Jlog6 = [[J, C J],[0, J]] as two explicit 3x3 matrices (row-major), built once per accepted
+// point, so that a column costs three matrix-vector products (27 fma) instead of the cross-product form (64):
+//   J = (1 - ce |w|^2) I + 1/2 [w]x + ce w w^T ,  C = da I + 1/2 [t]x + cv w^T + ce w t^T   (task_col's operators)
+DEV void task_mats(const ErrCoef& c, double* J, double* CJ) {
+  const v3 w = c.w, t = c.xt, cv = c.cv;
+  const double ce = c.ce;
+  const double a = fma(-ce, dot3(w, w), 1.0);
+  const double cxy = ce * (w.x * w.y), cxz = ce * (w.x * w.z), cyz = ce * (w.y * w.z);
+  J[0] = fma(ce, w.x * w.x, a); J[1] = fma(-0.5, w.z, cxy);   J[2] = fma(0.5, w.y, cxz);
+  J[3] = fma(0.5, w.z, cxy);    J[4] = fma(ce, w.y * w.y, a); J[5] = fma(-0.5, w.x, cyz);
+  J[6] = fma(-0.5, w.y, cxz);   J[7] = fma(0.5, w.x, cyz);    J[8] = fma(ce, w.z * w.z, a);
+  const v3 cw = scale3(w, ce);
+  double C[9];
+  C[0] = fma(cv.x, w.x, cw.x * t.x) + c.da;          C[1] = fma(cv.x, w.y, fma(cw.x, t.y, -0.5 * t.z)); C[2] = fma(cv.x, w.z, fma(cw.x, t.z, 0.5 * t.y));
+  C[3] = fma(cv.y, w.x, fma(cw.y, t.x, 0.5 * t.z));  C[4] = fma(cv.y, w.y, cw.y * t.y) + c.da;          C[5] = fma(cv.y, w.z, fma(cw.y, t.z, -0.5 * t.x));
+  C[6] = fma(cv.z, w.x, fma(cw.z, t.x, -0.5 * t.y)); C[7] = fma(cv.z, w.y, fma(cw.z, t.y, 0.5 * t.x));  C[8] = fma(cv.z, w.z, cw.z * t.z) + c.da;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) CJ[3 * i + k] = fma(C[3 * i], J[k], fma(C[3 * i + 1], J[3 + k], C[3 * i + 2] * J[6 + k]));
+}
+DEV void task_col_m(const double* J, const double* CJ, v3 lin, v3 ang, v3& top, v3& bot) {
+  double tp[3], bt[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    bt[i] = fma(J[3 * i], ang.x, fma(J[3 * i + 1], ang.y, J[3 * i + 2] * ang.z));
+    tp[i] = fma(J[3 * i], lin.x, fma(J[3 * i + 1], lin.y, fma(J[3 * i + 2], lin.z,
+            fma(CJ[3 * i], ang.x, fma(CJ[3 * i + 1], ang.y, CJ[3 * i + 2] * ang.z)))));
+  }
+  top = mk3(tp[0], tp[1], tp[2]);
+  bot = mk3(bt[0], bt[1], bt[2]);
+}
+
 DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Stage the chain blob into shared memory with one 1-D TMA bulk copy (thread 0 issues, everyone waits on the mbarrier).

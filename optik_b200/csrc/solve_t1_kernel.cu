@@ -5,6 +5,8 @@
 //   * one BACKWARD recursion in the target's frame on the inverse pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip)
 //     yields joint j's body-Jacobian column [t_C x (R_C a_j); R_C a_j] = [R_Bj^T (a_j x p_Bj); R_Bj^T a_j] with one
 //     rotation and one cross product, and the pose error X = C_0^-1  (as eval_kernel)
+//   * on accept the body columns become task columns by two explicit 3x3 matrices (Jlog6 = [[J, C J],[0, J]], 27 fma
+//     per column)
 //   * columns live in a per-thread shared-memory row (128-bit accesses, odd 16-byte row stride => conflict-free);
 //     two rows per thread: the current point's task columns and the trial point's body columns (swapped on accept)
 //   * the 6x6 Gram matrix is accumulated joint by joint with fma; the LDL^T solve is thread-private.
@@ -317,11 +319,13 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
       fc = ft; have_cur = 1;
 #pragma unroll
       for (int i = 0; i < 6; i++) rc[i] = rt[i];
+      double Jm[9], CJ[9];
+      task_mats(ec, Jm, CJ);
 #pragma unroll 1
       for (int j = 0; j < n; j++) {
         const double2 a0 = trow[3 * j + 0], a1 = trow[3 * j + 1], a2 = trow[3 * j + 2];
         v3 top, bot;
-        task_col(ec, mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), top, bot);
+        task_col_m(Jm, CJ, mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), top, bot);
         if (P.weighted) { top = weight3(tq, P.wl, top); bot = weight3(tq, P.wa, bot); }
         trow[3 * j + 0] = make_double2(top.x, top.y);
         trow[3 * j + 1] = make_double2(top.z, bot.x);

@@ -166,6 +166,37 @@ static void task_col(const err_coef* c, v3 lin, v3 ang, v3* top, v3* bot) {
   *bot = ja;
 }
 
+/* Thread-per-seed layout: Jlog6 = [[J, C J],[0, J]] as two explicit 3x3 matrices (row-major), built once per accepted
+ * point, so that a column costs three matrix-vector products (27 fma) instead of the cross-product form above (64).
+ *   J  = (1 - ce |w|^2) I + 1/2 [w]x + ce w w^T
+ *   C  = da I + 1/2 [t]x + cv w^T + ce w t^T         (same operator as task_col's C u) */
+static void task_mats(const err_coef* c, double J[9], double CJ[9]) {
+  v3 w = c->w, t = c->xt, cv = c->cv;
+  double ce = c->ce;
+  double a = fma(-ce, v3_dot(w, w), 1.0);
+  double cxy = ce * (w.x * w.y), cxz = ce * (w.x * w.z), cyz = ce * (w.y * w.z);
+  J[0] = fma(ce, w.x * w.x, a); J[1] = fma(-0.5, w.z, cxy);   J[2] = fma(0.5, w.y, cxz);
+  J[3] = fma(0.5, w.z, cxy);    J[4] = fma(ce, w.y * w.y, a); J[5] = fma(-0.5, w.x, cyz);
+  J[6] = fma(-0.5, w.y, cxz);   J[7] = fma(0.5, w.x, cyz);    J[8] = fma(ce, w.z * w.z, a);
+  v3 cw = v3_scale(w, ce);
+  double C[9];
+  C[0] = fma(cv.x, w.x, cw.x * t.x) + c->da;        C[1] = fma(cv.x, w.y, fma(cw.x, t.y, -0.5 * t.z)); C[2] = fma(cv.x, w.z, fma(cw.x, t.z, 0.5 * t.y));
+  C[3] = fma(cv.y, w.x, fma(cw.y, t.x, 0.5 * t.z)); C[4] = fma(cv.y, w.y, cw.y * t.y) + c->da;         C[5] = fma(cv.y, w.z, fma(cw.y, t.z, -0.5 * t.x));
+  C[6] = fma(cv.z, w.x, fma(cw.z, t.x, -0.5 * t.y)); C[7] = fma(cv.z, w.y, fma(cw.z, t.y, 0.5 * t.x)); C[8] = fma(cv.z, w.z, cw.z * t.z) + c->da;
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) CJ[3 * i + k] = fma(C[3 * i], J[k], fma(C[3 * i + 1], J[3 + k], C[3 * i + 2] * J[6 + k]));
+}
+static void task_col_m(const double J[9], const double CJ[9], v3 lin, v3 ang, v3* top, v3* bot) {
+  double tp[3], bt[3];
+  for (int i = 0; i < 3; i++) {
+    bt[i] = fma(J[3 * i], ang.x, fma(J[3 * i + 1], ang.y, J[3 * i + 2] * ang.z));
+    tp[i] = fma(J[3 * i], lin.x, fma(J[3 * i + 1], lin.y, fma(J[3 * i + 2], lin.z,
+            fma(CJ[3 * i], ang.x, fma(CJ[3 * i + 1], ang.y, CJ[3 * i + 2] * ang.z)))));
+  }
+  *top = v3_make(tp[0], tp[1], tp[2]);
+  *bot = v3_make(bt[0], bt[1], bt[2]);
+}
+
 /* tip handling rule (depends on n only, so every tile width gives the same bits): the fixed tip transform rides
  * the scan as entry n unless n is exactly a tile width (8, 16, 32), where no spare lane exists. */
 static int tip_in_scan(int n) { return !(n == 8 || n == 16 || n == 32); }
@@ -429,9 +460,11 @@ static int twin_attempt_t1(const twin_chain* c, const twin_params* P, se3t tgt, 
       memcpy(qc, qt_, sizeof(double) * n);
       memcpy(rc, rt, sizeof(rc));
       fc = ft; have_cur = 1;
+      double Jm[9], CJ[9];
+      task_mats(&ec, Jm, CJ);
       for (int j = 0; j < n; j++) {
         v3 top, bot;
-        task_col(&ec, v3_make(body[j][0], body[j][1], body[j][2]), v3_make(body[j][3], body[j][4], body[j][5]), &top, &bot);
+        task_col_m(Jm, CJ, v3_make(body[j][0], body[j][1], body[j][2]), v3_make(body[j][3], body[j][4], body[j][5]), &top, &bot);
         if (P->weighted) { top = weight3(tgt.q, P->wl, top); bot = weight3(tgt.q, P->wa, bot); }
         C[j][0] = top.x; C[j][1] = top.y; C[j][2] = top.z; C[j][3] = bot.x; C[j][4] = bot.y; C[j][5] = bot.z;
       }
