@@ -122,12 +122,16 @@ class HostStepPipeline:
                 "h_out": (pin((self.R, n), torch.float64), pin((self.R,), torch.float64), pin((self.R,), torch.int32), pin((self.R,), torch.int32)),
                 "record": d((RECORD_HEAD + n,), torch.float64), "gathered": d((world, RECORD_HEAD + n), torch.float64),
                 "best": d((RECORD_HEAD + n,), torch.float64), "h_best": pin((RECORD_HEAD + n,), torch.float64),
+                "busy": False,
             })
 
     def submit(self, slot, target, x0):
         """target (8,), x0 (n,): host arrays; copied into the slot's pinned buffers, then everything is enqueued."""
         import torch
         s = self.slots[slot]
+        if s["busy"]:  # the slot's pinned buffers are still owned by its previous step
+            s["stream"].synchronize()
+        s["busy"] = True
         s["h_in"][0].numpy()[:] = target
         s["h_in"][1].numpy()[:] = x0
         with torch.cuda.stream(s["stream"]):
@@ -144,4 +148,5 @@ class HostStepPipeline:
         """Waits for the slot's step; returns (q, f, status, evals, global_best_record) as numpy views of pinned memory."""
         s = self.slots[slot]
         s["stream"].synchronize()
+        s["busy"] = False
         return tuple(h.numpy() for h in s["h_out"]) + (s["h_best"].numpy(),)

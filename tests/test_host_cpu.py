@@ -184,3 +184,33 @@ def test_cpp_consumer_with_its_own_declarations_links_and_runs(tmp_path):
     base, ee = ob.ROBOT_LINKS["ur3e"]
     p = subprocess.run([str(exe), ob.data_path("ur3e"), base, ee, "cpu"], capture_output=True, text=True)
     assert p.returncode == 0 and "n=6 inside=1" in p.stdout, p.stdout + p.stderr
+
+
+def test_new_entry_points_check_their_arguments_before_touching_the_gpu():
+    """Shape / mode errors of the batched additions surface as Python exceptions on a machine without a GPU."""
+    r = ob.Robot.named("ur3e")
+    with pytest.raises(ValueError):
+        r.diff_ik([0.0] * 5, [0.0] * 6, [1.0] * 6)            # len(x0) != num_positions (crates/optik-py/src/lib.rs:143)
+    with pytest.raises(ValueError):
+        r.diff_ik([0.0] * 6, [0.0] * 6, [1.0] * 5)            # len(v_max) != num_positions (:144-148)
+    with pytest.raises(ValueError):
+        r.diff_ik([0.0] * 6, [0.0] * 5, [1.0] * 6)
+    with pytest.raises(ValueError):
+        r.diff_ik_batch(np.zeros((3, 5)), np.zeros(6), np.ones(6))
+    with pytest.raises(ValueError):
+        r.diff_ik_batch(np.zeros((3, 6)), np.zeros((2, 6)), np.ones(6))
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=4)
+    with pytest.raises(ValueError):
+        r.ik_attempts(cfg, np.zeros(8), np.zeros(6), 4, wait=False)   # asynchronous call without a stream
+    with pytest.raises(ValueError):
+        r.ik_batch(cfg, np.zeros((2, 8)), np.zeros((2, 6)), restarts=4, wait=False)
+    with pytest.raises(ValueError):
+        r.ik_batch(cfg, np.zeros((2, 7)), np.zeros((2, 6)), restarts=4)
+
+
+def test_batch_opts_flags_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "optik_b200.h")).read()
+    for name, val in (("OPTIK_BATCH_ASYNC", ob.BATCH_ASYNC), ("OPTIK_BATCH_PHASED", ob.BATCH_PHASED),
+                      ("OPTIK_BATCH_SINGLE_LAUNCH", ob.BATCH_SINGLE_LAUNCH)):
+        assert f"#define {name} {val}u" in hdr
+    assert f"#define OPTIK_RECORD_HEAD {ob.RECORD_HEAD}" in hdr
