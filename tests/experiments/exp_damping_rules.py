@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0,"/root/repo")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle as O
 ch=O.Chain.from_urdf(open("/root/repo/optik_b200/data/panda.urdf").read(),"panda_link0","panda_link8")
 P=O.twin_params()

@@ -1,5 +1,5 @@
 import sys, numpy as np, itertools
-sys.path.insert(0,"/root/repo")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from exp2 import run
 names=sys.argv[1].split(",")
 for rel,cnt in [(0,1000),(1e-3,2),(1e-3,3),(1e-2,2),(1e-2,3),(5e-2,2),(5e-2,3),(1e-1,3),(1e-1,4),(2e-1,4)]:

@@ -1,5 +1,5 @@
 import sys, numpy as np, time
-sys.path.insert(0,"/root/repo")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import oracle as O
 robots={"panda":("panda_link0","panda_link8"),"ur5":("base_link","ee_link"),"ur3e":("ur_base_link","ur_ee_link"),"snake20":("seg0","tip")}
 def run(name, R=2000, ntgt=3, **lm):
