@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEEDS_PER_GPU = 65536
+CPU_BASELINE_STEPS = 32  # cpu_baseline sample: 32 full steps (2 Mi attempts, ~20 CPU-seconds on 16 cores)
 E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "2"))  # host-buffer calls in flight on one GPU
 E2E_DEPTH_MULTI = 4  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
@@ -364,9 +365,9 @@ def run_product(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cconv, csecs, catt = cpu_reference_steps(8, 1, threads)
+            cconv, csecs, catt = cpu_reference_steps(CPU_BASELINE_STEPS, 2, threads)
             cpu = {"value": cconv / csecs, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"8 steps x {SEEDS_PER_GPU} seeds to one target each ({int(catt)} attempts, {csecs:.2f} s wall); "
+                   "sample": f"{CPU_BASELINE_STEPS} steps x {SEEDS_PER_GPU} seeds to one target each ({int(catt)} attempts, {csecs:.2f} s wall); "
                              "oracle port of the rayon restart loop over the fp64 LM twin (the Rust reference cannot be built here)"}
         value = verified / (dev_ms * 1e-3)
         solve_bytes = 8 * (2 * n + 4)  # per attempt: q + f out, status/evals, target amortised
