@@ -61,8 +61,9 @@ optik_robot* optik_robot_from_urdf_file(const char* path, const char* base_link,
 optik_robot* optik_robot_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link);
 /* crates/optik-cpp/src/lib.rs:52-57 */
 void optik_robot_free(optik_robot* robot);
-/* crates/optik-cpp/src/lib.rs:59-65.  rayon thread count in the reference; here it only bounds the number of
- * host threads that may stage work concurrently (the restart fan-out is the CUDA grid). */
+/* crates/optik-cpp/src/lib.rs:59-65.  rayon thread count in the reference.  Here the restart fan-out is the CUDA grid:
+ * the value is stored and otherwise has no effect (results never depend on it -- the per-target answer is always the
+ * one the reference gives with set_parallelism(1), see optik_gpu_ik_batch). */
 void optik_robot_set_parallelism(optik_robot* robot, unsigned int n);
 /* crates/optik-cpp/src/lib.rs:67-73 */
 unsigned int optik_robot_num_positions(const optik_robot* robot);
@@ -79,8 +80,9 @@ double* optik_robot_fk(const optik_robot* robot, const double* x);
  * Aborts with "seed joint position outside of joint limits" like lib.rs:251-254. */
 double* optik_robot_ik(const optik_robot* robot, const optik_solver_config* config, const double* target,
                        const double* x0);
-/* crates/optik-cpp/src/lib.rs:164-183.  Out of scope of this build (Clarabel LP):
- * always returns NULL ("no solution") after printing a one-time notice. */
+/* crates/optik-cpp/src/lib.rs:164-183.  n doubles (joint velocities; alpha is dropped like the reference's wrapper
+ * does) or NULL when there is no solution.  Runs the batched diff_ik kernel on one configuration: the reference's LP
+ * (lib.rs:123-239) solved exactly instead of by Clarabel's interior-point iteration; num_positions 6 or 7. */
 double* optik_robot_diff_ik(const optik_robot* robot, const double* x0, const double* V_WE, const double* v_max);
 
 /* ------------------------------------------------------------------------
@@ -109,6 +111,11 @@ enum {
   OPTIK_STATUS_NAN = 6,
   OPTIK_STATUS_SKIPPED = 7
 };
+/* status words are `code | flags`.  Device-memory batched calls cannot reject a seed outside the joint limits without
+ * a host sync (the reference panics, lib.rs:251-254; host-memory calls return OPTIK_ERR_SEED_LIMITS): the seed is
+ * clamped into the limits and the target's status carries this flag. */
+#define OPTIK_STATUS_CODE_MASK 0xff
+#define OPTIK_STATUS_FLAG_SEED_CLAMPED 0x100
 
 const char* optik_last_error(void);
 /* Non-aborting constructors (NULL + optik_last_error() on failure). */
@@ -148,7 +155,8 @@ typedef struct optik_gpu_batch_opts {
    * This is the record ranks exchange for a cross-GPU best-pick (optik_gpu_select_records). */
   double* best_record_out;
   uint32_t flags;          /* OPTIK_BATCH_* bits */
-  uint32_t reserved;
+  uint32_t variant;        /* thread-per-seed kernel: 0 = default, 1 = trial columns in local memory (3 blocks/SM),
+                              2 = in shared memory (2 blocks/SM); same results bit for bit */
 } optik_gpu_batch_opts;
 
 /* opts->flags.  OPTIK_BATCH_ASYNC (host-memory calls only, `stream` must be non-NULL): enqueue the H2D copies, the
@@ -157,23 +165,28 @@ typedef struct optik_gpu_batch_opts {
  * (optik_host_alloc), otherwise the copies are staged synchronously.  Two streams with two sets of buffers overlap
  * one call's transfers with the next call's kernels.  opts->counters is then SET (not incremented). */
 #define OPTIK_BATCH_ASYNC 1u
-/* Speed-mode optik_gpu_ik_batch in PHASES: restarts [0,2) of every target in one launch, then the still-unsolved
- * targets are compacted on the device and only they run further restarts (in order while they fill the GPU, in
- * parallel chunks with early exit afterwards).  Same per-target result (lowest-index converged restart, lib.rs:409-412),
- * no geometric tail of unlucky targets: 1.3-2x the throughput of one launch.  Each phase boundary synchronises the
- * stream to size the next launch, so DEVICE-memory calls (documented as asynchronous) only do this when asked with
- * OPTIK_BATCH_PHASED; blocking HOST-memory calls always do, unless OPTIK_BATCH_SINGLE_LAUNCH is set. */
-#define OPTIK_BATCH_PHASED 2u
-#define OPTIK_BATCH_SINGLE_LAUNCH 4u
+/* Speed-mode batches of the thread-per-seed kernel normally run as DYNAMIC CHAINS in one launch: a lane that takes a
+ * target claims its restarts one by one on the device; once every target has been taken, idle lanes claim further
+ * restarts of the still-unsolved targets in parallel.  A claimed restart always runs unless a lower index of the same
+ * target has converged, so the per-target result is the lowest-index converged restart (lib.rs:409-412) whatever the
+ * timing.  OPTIK_BATCH_STATIC forces the static (target, chunk) schedule instead (same results; evals_out is then
+ * reproducible, with dynamic chains it includes speculative attempts). */
+#define OPTIK_BATCH_STATIC 8u
 
 #define OPTIK_RECORD_HEAD 8
 
 /* Robot::ik() over T independent (target, x0) pairs in one launch.
  *   targets [T][8] pose8, x0 [T][n]  ->  q_out [T][n], cost_out [T] (objective value), status_out [T]
- * Per target the result is what the reference returns with set_parallelism(1): Speed = the lowest-index
- * converged restart (lib.rs:409-412), Quality = arg-min ||q - x0|| over converged restarts (lib.rs:398-407);
- * status_out[t] is the winning attempt's status, or a failure status when none converged (== None).
- * config->max_time > 0 bounds the whole launch (device-side deadline, checked per evaluation like lib.rs:308). */
+ * Per target the SELECTION follows the reference with set_parallelism(1): Speed = the lowest-index converged restart
+ * (lib.rs:409-412), Quality = arg-min ||q - x0|| over converged restarts (lib.rs:398-407).  The numerical solution
+ * of a restart is the in-kernel Levenberg-Marquardt iterate, not NLopt SLSQP's (replaced by design, DESIGN.md
+ * section 3): it satisfies the reference's success predicate f(q) < tol_f inside the limits, it is not bit-equal to
+ * what the reference would return.  status_out[t] is the winning attempt's status, or a failure status when none
+ * converged (== None).
+ * Budgets as in the reference (lib.rs:260-277): config->max_time > 0 bounds the whole launch (device-side deadline,
+ * checked per evaluation like lib.rs:308); restarts = opts->restarts, else config->max_restarts, and with
+ * max_restarts == 0 (the reference's default, "no limit") restarts are drawn until max_time expires -- max_time == 0
+ * together with no restart limit is refused like crates/optik-py/src/lib.rs:45-47. */
 int optik_gpu_ik_batch(const optik_robot* robot, const optik_solver_config* config, const optik_gpu_batch_opts* opts,
                        const double* targets, const double* x0, uint64_t T, double* q_out, double* cost_out,
                        int32_t* status_out, void* stream);
@@ -212,6 +225,15 @@ int optik_robot_diff_ik_ex(const optik_robot* robot, const double* x0, const dou
  * semantics as optik_robot_ik.  Returns 1 = solution written to q_out[n], *cost_out; 0 = no solution; <0 = -(error). */
 int optik_robot_ik_ex(const optik_robot* robot, const optik_solver_config* config, const double* target_pose8,
                       const double* x0, const double* ee_offset_pose8, double* q_out, double* cost_out);
+
+/* The restart seeds the solver uses (lib.rs:86-91, 360-370): seeds_out[i][j] for restart indices
+ * [restart_begin, restart_begin + count), restart_begin >= 1 (restart 0 is the caller's x0), written by the same
+ * kernel that fills the solve kernels' seed table.  memory: 0 host, 1 device (asynchronous on `stream`). */
+int optik_gpu_restart_seeds(const optik_robot* robot, uint64_t restart_begin, uint64_t count, int memory, double* seeds_out,
+                            void* stream);
+/* Known-answer hook for the seed generator: the 16 output words of the ChaCha8 block (block counter 0) of stream
+ * `stream_id` under `key8`, computed by the device function the kernels use.  Host pointers, blocking. */
+int optik_gpu_chacha8_block(const optik_robot* robot, const uint32_t* key8, uint64_t stream_id, uint32_t* words16_out);
 
 /* Cross-GPU best-pick: the reference's selection rule (lib.rs:397-413) over `count` candidate records of
  * OPTIK_RECORD_HEAD + n doubles (e.g. the output of an all-gather): converged first, then lowest score, then lowest

@@ -40,10 +40,11 @@ class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
                 ("chunks", C.c_uint32), ("tile", C.c_uint32), ("max_evals", C.c_uint32), ("blocks", C.c_uint32),
                 ("memory", C.c_int32), ("ee_offset", C.c_void_p), ("restart_out", C.c_void_p),
                 ("evals_out", C.c_void_p), ("counters", C.c_void_p), ("best_record_out", C.c_void_p),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("variant", C.c_uint32)]
 
 
-BATCH_ASYNC, BATCH_PHASED, BATCH_SINGLE_LAUNCH = 1, 2, 4  # == OPTIK_BATCH_*
+BATCH_ASYNC, BATCH_STATIC = 1, 8  # == OPTIK_BATCH_*
+STATUS_CODE_MASK, STATUS_FLAG_SEED_CLAMPED = 0xff, 0x100  # == OPTIK_STATUS_*
 
 
 RECORD_HEAD = 8  # candidate record: [found, score, restart, cost, status, 0, 0, 0, q...]
@@ -93,6 +94,8 @@ def load_library():
         "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
         "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
         "optik_gpu_select_records": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "optik_gpu_restart_seeds": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, vp, vp]),
+        "optik_gpu_chacha8_block": (C.c_int, [vp, vp, C.c_uint64, vp]),
         "optik_gpu_diff_ik_batch": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_uint64, vp, C.c_int, vp, vp, vp, vp]),
         "optik_robot_diff_ik_ex": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(C.c_double), vp]),
         "optik_gpu_stream_create": (C.c_int, [vp, C.POINTER(vp)]),
@@ -199,7 +202,7 @@ class SolverConfig:
 
     def is_success(self, status):
         """lib.rs:376-379 applied to a status code array."""
-        st = np.asarray(status)
+        st = np.asarray(status) & STATUS_CODE_MASK
         return ((self.tol_f >= 0) & (st == 1)) | ((self.tol_df >= 0) & (st == 2)) | ((self.tol_dx >= 0) & (st == 3))
 
 
@@ -415,8 +418,10 @@ class Robot:
         return alpha, v, st
 
     # ---- batched additions --------------------------------------------------------------------
-    def _opts(self, memory, restarts=0, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0, ee_offset=None):
+    def _opts(self, memory, restarts=0, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0, ee_offset=None,
+              variant=0):
         o = _BatchOpts()
+        o.variant = int(variant)
         o.struct_size = C.sizeof(_BatchOpts)
         o.restarts, o.restart_begin, o.chunks, o.tile = int(restarts), int(restart_begin), int(chunks), int(tile)
         o.max_evals, o.blocks, o.memory = int(max_evals), int(blocks), int(memory)
@@ -429,7 +434,7 @@ class Robot:
         return o, keep
 
     def ik_batch(self, config, targets, x0, restarts=None, restart_begin=0, chunks=0, tile=0, max_evals=0, blocks=0,
-                 ee_offset=None, stats=False, out=None, stream=None, wait=True, phased=None):
+                 ee_offset=None, stats=False, out=None, stream=None, wait=True, static=False, variant=0):
         """Robot::ik over T (target, x0) pairs in one launch.
 
         targets: (T, 8) pose8 rows {qx,qy,qz,qw,tx,ty,tz,0};  x0: (T, n).
@@ -437,9 +442,10 @@ class Robot:
         torch CUDA tensors in -> device path on torch's current stream, returns torch tensors (no sync).
         Host path with stream=<Stream> and wait=False: returns as soon as everything is enqueued; the outputs (give
         pinned `out` buffers, see pinned_empty) are valid after stream.synchronize().
-        phased: Speed-mode batches in phases (OPTIK_BATCH_PHASED: unsolved targets are compacted between launches --
-        same results, no tail of unlucky targets, but one stream sync per phase).  Default: on for blocking host
-        calls, off for device-tensor calls (which stay fully asynchronous); True / False force it.
+        restarts=None: config.max_restarts; with the reference's default (no restart limit) restarts are drawn until
+        config.max_time expires (lib.rs:260-277).
+        static=True forces the static (target, chunk) schedule for Speed batches (OPTIK_BATCH_STATIC) instead of the
+        dynamic chains -- same q / cost / status / winning restart, reproducible `evals`.
         """
         lib = load_library()
         c = config._c()
@@ -458,9 +464,9 @@ class Robot:
                 st = torch.empty((T,), dtype=torch.int32, device=dev)
             else:
                 q, f, st = out
-            o, keep = self._opts(1, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
-            if phased:
-                o.flags |= BATCH_PHASED
+            o, keep = self._opts(1, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset, variant)
+            if static:
+                o.flags |= BATCH_STATIC
             extra = {}
             if stats:
                 extra["restart"] = torch.empty((T,), dtype=torch.int64, device=dev)
@@ -480,14 +486,14 @@ class Robot:
             q, f, st = np.empty((T, n)), np.empty(T), np.empty(T, dtype=np.int32)
         else:
             q, f, st = out
-        o, keep = self._opts(0, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset)
+        o, keep = self._opts(0, restarts, restart_begin, chunks, tile, max_evals, blocks, ee_offset, variant)
         sh = _stream_handle(stream)
         if not wait:
             if sh is None:
                 raise ValueError("wait=False needs a stream")
             o.flags |= BATCH_ASYNC
-        if phased is False:
-            o.flags |= BATCH_SINGLE_LAUNCH
+        if static:
+            o.flags |= BATCH_STATIC
         extra = {}
         if stats:
             extra["restart"] = np.zeros(T, dtype=np.uint64)
@@ -499,7 +505,7 @@ class Robot:
         return (q, f, st, extra) if stats else (q, f, st)
 
     def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None,
-                    best=False, out=None, counters=None, record=None, stream=None, wait=True):
+                    best=False, out=None, counters=None, record=None, stream=None, wait=True, variant=0):
         """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
         completion (no Speed-mode early exit) -- BASELINE config 2's output.  best=True also runs the selection
         pass (lib.rs:397-413) and appends the packed candidate record (RECORD_HEAD + n doubles:
@@ -510,7 +516,7 @@ class Robot:
         lib = load_library()
         c = config._c()
         n, R = self._n, int(restarts)
-        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset)
+        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset, variant)
         if _is_torch(target):
             import torch
             dev = target.device
@@ -554,6 +560,20 @@ class Robot:
         _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.ctypes.data, x0.ctypes.data,
                                          q.ctypes.data, f.ctypes.data, st.ctypes.data, ev.ctypes.data, sh))
         return (q, f, st, ev, record) if best else (q, f, st, ev)
+
+    def restart_seeds(self, restart_begin, count):
+        """The solver's restart seeds (lib.rs:86-91, 360-370) for indices [restart_begin, restart_begin+count), (count, n)."""
+        out = np.zeros((int(count), self._n))
+        _check(load_library().optik_gpu_restart_seeds(self._h, int(restart_begin), int(count), 0, out.ctypes.data, None))
+        return out
+
+    def chacha8_block(self, key8, stream_id):
+        """Known-answer hook: 16 output words of the kernels' ChaCha8 block function (block counter 0)."""
+        key = np.ascontiguousarray(key8, dtype=np.uint32)
+        assert key.shape == (8,)
+        out = np.zeros(16, dtype=np.uint32)
+        _check(load_library().optik_gpu_chacha8_block(self._h, key.ctypes.data, int(stream_id), out.ctypes.data))
+        return out
 
     def select_records(self, records, out=None):
         """Best-pick (lib.rs:397-413) over gathered candidate records (W, RECORD_HEAD+n) CUDA tensor -> one record."""

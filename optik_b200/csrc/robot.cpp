@@ -30,18 +30,21 @@ extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n, int cols);
-extern "C" int optik_launch_compact_unsolved(const int* status, unsigned long long T, double tol_f, double tol_df_user,
-                                             double tol_dx, unsigned* list, unsigned* count, void* stream);
 extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stream);
 extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm);
-extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream);
-extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm);
+extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows, int blocks, void* stream);
+extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm);
+extern "C" int optik_launch_seed_table(const double* chain, int n, const uint32_t* key_dev, unsigned long long r_begin,
+                                       unsigned long long count, double* out, void* stream);
+extern "C" int optik_launch_chacha8_kat(const uint32_t* key_dev, unsigned long long stream_id, uint32_t* out16_dev, void* stream);
+extern "C" int optik_launch_flag_clamped(const double* chain, int n, const double* x0, unsigned long long T, int* status,
+                                         unsigned long long status_stride, void* stream);
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
 
 namespace {
 
 thread_local std::string g_last_error;
-bool g_urdf_correct_fold = false;
+std::atomic<bool> g_urdf_correct_fold{false};
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -69,6 +72,8 @@ void seed_key_from_u64(uint64_t state, uint32_t key[8]) {
   }
 }
 const uint64_t RNG_SEED = 42;  // lib.rs:359
+constexpr unsigned long long SEED_CACHE = 4096;           // restart indices whose seeds every robot keeps resident
+constexpr unsigned long long SEED_TABLE_MAX = 1ull << 21;  // largest per-call seed table (restarts)
 
 void pose8_identity(double* p) {
   for (int i = 0; i < 8; i++) p[i] = 0;
@@ -137,15 +142,19 @@ struct optik_robot {
   mutable uint32_t chain_bytes = 0;
   mutable int sm_count = 0;
   mutable int occ[3] = {0, 0, 0};  // resident blocks/SM for TILE 8,16,32
-  mutable int occ_t1 = 0;          // resident blocks/SM of the thread-per-seed kernel (n <= 8)
+  mutable int occ_t1[2] = {0, 0};  // resident blocks/SM of the thread-per-seed kernel (n <= 8): rows = 1, rows = 2
   mutable DevBuf scratch;          // single-call scratch (ik / fk / jacobian), guarded by mu
   mutable cudaStream_t stream = nullptr;
   mutable void* pinned = nullptr;
   mutable size_t pinned_cap = 0;
+  mutable cudaMemPool_t pool = nullptr;  // library-owned stream-ordered pool (the process's default pool is left alone)
+  mutable DevBuf key_dev;                // ChaCha8 key = seed_from_u64(42), 8 words
+  mutable DevBuf seed_cache;             // restart seeds for indices [0, SEED_CACHE) (lib.rs:360-370)
 
   ~optik_robot() {
     if (stream) cudaStreamDestroy(stream);
     if (pinned) cudaFreeHost(pinned);
+    if (pool) cudaMemPoolDestroy(pool);
   }
   void finish_init() {
     n = 0;
@@ -201,14 +210,31 @@ struct optik_robot {
     sm_count = prop.multiProcessorCount;
     const int tiles[3] = {8, 16, 32};
     for (int i = 0; i < 3; i++) CUDA_TRY(optik_solve_occupancy(tiles[i], &occ[i]));
-    if (n <= 8) CUDA_TRY(optik_solve_t1_occupancy(n, &occ_t1));
+    if (n <= 8) {
+      CUDA_TRY(optik_solve_t1_occupancy(n, 1, &occ_t1[0]));
+      CUDA_TRY(optik_solve_t1_occupancy(n, 2, &occ_t1[1]));
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    // keep stream-ordered scratch cached across synchronisations (the default threshold of 0 returns it to the
-    // driver at every sync, which turns each host-path call into a fresh cudaMalloc)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // stream-ordered scratch comes from a pool this robot owns; its release threshold keeps blocks cached across
+    // synchronisations (with the default of 0 every host-path call would turn into a fresh cudaMalloc)
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CUDA_TRY(cudaMemPoolCreate(&pool, &props));
+    unsigned long long keep = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // ChaCha8 key and the restart seeds every call shares (restart i >= 1 is the same draw for every target)
+    uint32_t key[8];
+    seed_key_from_u64(RNG_SEED, key);
+    if (key_dev.reserve(sizeof(key))) return fail(OPTIK_ERR_CUDA, "cudaMalloc(key) failed");
+    CUDA_TRY(cudaMemcpy(key_dev.p, key, sizeof(key), cudaMemcpyHostToDevice));
+    if (n <= 8) {
+      if (seed_cache.reserve((size_t)SEED_CACHE * n * sizeof(double))) return fail(OPTIK_ERR_CUDA, "cudaMalloc(seeds) failed");
+      CUDA_TRY(optik_launch_seed_table((const double*)chain_dev.p, n, (const uint32_t*)key_dev.p, 0, SEED_CACHE,
+                                       (double*)seed_cache.p, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
     }
     gpu_ready = true;
     return 0;
@@ -227,7 +253,7 @@ optik_robot* robot_from_chain(std::vector<optik::Joint>&& joints) {
 optik_robot* try_from_urdf_str(const char* urdf, const char* base, const char* ee) {
   try {
     if (!urdf || !base || !ee) throw std::runtime_error("null argument");
-    return robot_from_chain(optik::chain_from_urdf(urdf, base, ee, g_urdf_correct_fold));
+    return robot_from_chain(optik::chain_from_urdf(urdf, base, ee, g_urdf_correct_fold.load()));
   } catch (const std::exception& e) {
     g_last_error = e.what();
     return nullptr;
@@ -235,7 +261,7 @@ optik_robot* try_from_urdf_str(const char* urdf, const char* base, const char* e
 }
 
 struct Plan {
-  int tile, blocks, tiles_per_block, resident_tiles;
+  int tile, blocks, tiles_per_block, resident_tiles, rows;
 };
 // lanes per restart seed: 1 = thread-per-seed kernel (n <= 8), 8/16/32 = tile kernel.  `batch`: auto picks the
 // throughput layout (1) when it exists, otherwise / for single-target latency the smallest tile that fits.
@@ -246,13 +272,20 @@ int choose_tile(int n, uint32_t want, bool batch) {
   if (batch && n <= 8) return 1;
   return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 }
-Plan make_plan(const optik_robot* r, int tile, uint32_t blocks_req, unsigned long long njobs) {
+// thread-per-seed kernel: rows = 2 keeps the trial columns in shared memory (2 blocks/SM), rows = 1 in local memory
+// (3 blocks/SM).  opts.variant forces one; the default is the measured better one.
+int t1_rows(const optik_gpu_batch_opts* o) {
+  if (o && (o->variant == 1 || o->variant == 2)) return (int)o->variant;
+  return OPTIK_T1_DEFAULT_ROWS;
+}
+Plan make_plan(const optik_robot* r, int tile, int rows, uint32_t blocks_req, unsigned long long njobs) {
   Plan p;
   p.tile = tile;
+  p.rows = rows;
   p.tiles_per_block = 128 / tile;
   const int oi = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
   int per_sm = r->occ[oi] > 0 ? r->occ[oi] : 1;
-  if (tile == 1) per_sm = r->occ_t1 > 0 ? r->occ_t1 : 1;
+  if (tile == 1) per_sm = r->occ_t1[rows - 1] > 0 ? r->occ_t1[rows - 1] : 1;
   const long long resident_blocks = (long long)r->sm_count * per_sm;  // one full wave: a multiple of the SM count
   p.resident_tiles = (int)(resident_blocks * p.tiles_per_block);
   long long need = (long long)((njobs + p.tiles_per_block - 1) / p.tiles_per_block);
@@ -293,26 +326,42 @@ bool config_valid(const optik_solver_config* c) {
   return c && (c->solution_mode == OPTIK_MODE_QUALITY || c->solution_mode == OPTIK_MODE_SPEED);
 }
 
-// Device-side batched solve on `stream`; every pointer is device memory.  Stream-ordered scratch.
+// stream-ordered scratch from the robot's pool, released (stream-ordered) on every exit path
+struct StreamBuf {
+  char* p = nullptr;
+  cudaStream_t s = nullptr;
+  cudaError_t alloc(const optik_robot* r, size_t bytes, cudaStream_t stream) {
+    s = stream;
+    return cudaMallocFromPoolAsync((void**)&p, bytes ? bytes : 1, r->pool, stream);
+  }
+  ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+constexpr uint64_t UNBOUNDED_RESTARTS = 0xfffffffeull;  // max_restarts == 0 with a max_time: restarts until the deadline
+
+// Device-side batched solve on `stream`; every pointer is device memory.  Stream-ordered scratch, no host sync.
 int solve_device(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
                  const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
                  double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
-                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr,
-                 const unsigned* d_tlist = nullptr, uint64_t chunks_override = 0) {
-  // d_tlist != null: a later phase of a phased batch -- the T targets of this launch are rows d_tlist[t] of
-  // d_targets / d_x0 and of every output; only converged winners replace what earlier phases recorded
+                 unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
   const int tile = choose_tile(r->n, o ? o->tile : 0, true);
   if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (num_positions <= 8), 8, 16 or 32 and >= num_positions");
+  const int rows = t1_rows(o);
   SolveParams P{};
   fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
   P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
-  P.tlist = d_tlist;
   P.max_ns = max_ns;
   P.counters = (unsigned long long*)d_counters;
-  // chunks per target
-  Plan plan0 = make_plan(r, tile, o ? o->blocks : 0, ~0ull);
-  uint64_t C = chunks_override ? chunks_override : (o ? o->chunks : 0);
+  const int n = r->n;
+  const bool speed = cfg->solution_mode == OPTIK_MODE_SPEED;
+  Plan plan0 = make_plan(r, tile, rows, o ? o->blocks : 0, ~0ull);
+  // ---- scheduling.  Speed batches of the thread-per-seed kernel with enough targets run as dynamic chains (one launch,
+  // restarts claimed on the device); everything else as static (target, chunk) jobs.
+  const bool dyn = tile == 1 && speed && !per_attempt_records && !(o && o->chunks) && !(o && (o->flags & OPTIK_BATCH_STATIC)) &&
+                   T * 8 >= (uint64_t)plan0.resident_tiles && T < 0xfffffffeull && R <= UNBOUNDED_RESTARTS;
+  uint64_t C = o ? o->chunks : 0;
   if (per_attempt_records) C = R;
+  if (dyn) C = 1;
   if (C == 0) {
     const uint64_t want = 2ull * (uint64_t)plan0.resident_tiles;
     C = T >= want ? 1 : (want + T - 1) / T;
@@ -324,42 +373,77 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const unsigned long long njobs = T * C;
   if (C > 1 && !per_attempt_records && T > 0x7fffffffull)
     return fail(OPTIK_ERR_INVALID, "T too large for a selection pass; use chunks = 1");
-  Plan plan = make_plan(r, tile, o ? o->blocks : 0, njobs);
-  const int n = r->n;
-  const bool direct = ((C == 1) || per_attempt_records) && !d_tlist;  // candidate records ARE the outputs
-  // scratch: optional outputs the caller did not ask for + candidate arrays when a selection pass follows
+  Plan plan = make_plan(r, tile, rows, o ? o->blocks : 0, njobs);
+  const bool direct = (C == 1) || per_attempt_records;  // candidate records ARE the outputs
+  // ---- scratch: optional outputs the caller did not ask for + candidate arrays when a selection pass follows
   size_t bytes = 0;
   auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
   const size_t off_q = direct ? 0 : carve(njobs * n * sizeof(double));
   const size_t off_f = direct ? 0 : carve(njobs * sizeof(double));
   const size_t off_st = direct ? 0 : carve(njobs * sizeof(int));
-  const size_t off_score = carve(njobs * sizeof(double));
+  const size_t off_score = dyn ? 0 : carve(njobs * sizeof(double));
   const bool restart_direct = direct && d_restart && !per_attempt_records;  // per-attempt: restart_out is the winner's
-  const size_t off_rs = restart_direct ? 0 : carve(njobs * sizeof(unsigned long long));
-  const size_t off_ev = (direct && d_evals) ? 0 : carve(njobs * sizeof(int));
-  const bool use_found = (cfg->solution_mode == OPTIK_MODE_SPEED) && C > 1 && !per_attempt_records;
+  const size_t off_rs = (restart_direct || dyn) ? 0 : carve(njobs * sizeof(unsigned long long));
+  const size_t off_ev = ((direct && d_evals) || dyn) ? 0 : carve(njobs * sizeof(int));
+  const bool use_found = speed && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
-  const size_t off_queue = carve(sizeof(unsigned long long));
+  // dynamic chains: [queue | ctl[3] | next[T] | lock[T] | ticket ring] zeroed together, found[T] set to ~0
+  unsigned help_cap = 1;
+  if (dyn) while (help_cap < 4u * (unsigned)plan0.resident_tiles) help_cap <<= 1;
+  const size_t off_zero = carve(dyn ? 32 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned) : sizeof(unsigned long long));
+  const size_t off_dfound = dyn ? carve(T * sizeof(unsigned)) : 0;
   // selection: slice the candidate range when one target has very many chunks
   unsigned slices = 1;
   if (C >= 4096) { slices = (unsigned)((C + 1023) / 1024); if (slices > 256) slices = 256; }
   const size_t off_part = slices > 1 ? carve((size_t)T * slices * optik_select_partial_bytes()) : 0;
-  char* scratch = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes, s));
-  P.cand_q = direct ? d_q : (double*)(scratch + off_q);
-  P.cand_f = direct ? d_f : (double*)(scratch + off_f);
-  P.cand_status = direct ? d_status : (int*)(scratch + off_st);
-  P.cand_score = (double*)(scratch + off_score);
-  P.cand_restart = restart_direct ? (unsigned long long*)d_restart : (unsigned long long*)(scratch + off_rs);
-  P.cand_evals = (direct && d_evals) ? d_evals : (int*)(scratch + off_ev);
-  P.queue = (unsigned long long*)(scratch + off_queue);
-  CUDA_TRY(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), s));
-  P.found = nullptr;
-  if (use_found) {
-    P.found = (unsigned long long*)(scratch + off_found);
-    CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
+  // restart seeds: the robot's resident table, a per-call table for long restart ranges, in-kernel draws beyond
+  size_t off_seed = 0;
+  bool own_table = false;
+  if (tile == 1) {
+    if (r_begin + R <= SEED_CACHE || R > SEED_TABLE_MAX) {
+      P.seed_tab = (const double*)r->seed_cache.p; P.seed_begin = 0; P.seed_count = SEED_CACHE;
+    } else {
+      own_table = true;
+      off_seed = carve((size_t)R * n * sizeof(double));
+    }
   }
-  if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, plan.blocks, s));
+  StreamBuf scratch;
+  CUDA_TRY(scratch.alloc(r, bytes, s));
+  char* sc = scratch.p;
+  if (own_table) {
+    P.seed_tab = (const double*)(sc + off_seed); P.seed_begin = r_begin; P.seed_count = R;
+    CUDA_TRY(optik_launch_seed_table(P.chain, n, (const uint32_t*)r->key_dev.p, r_begin, R, (double*)(sc + off_seed), s));
+  }
+  P.cand_q = direct ? d_q : (double*)(sc + off_q);
+  P.cand_f = direct ? d_f : (double*)(sc + off_f);
+  P.cand_status = direct ? d_status : (int*)(sc + off_st);
+  P.cand_score = dyn ? nullptr : (double*)(sc + off_score);
+  P.cand_restart = (restart_direct || dyn) ? (unsigned long long*)d_restart : (unsigned long long*)(sc + off_rs);
+  P.cand_evals = ((direct && d_evals) || dyn) ? d_evals : (int*)(sc + off_ev);
+  P.queue = (unsigned long long*)(sc + off_zero);
+  P.found = nullptr;
+  if (dyn) {
+    P.sched = 1;
+    P.dyn_ctl = (unsigned long long*)(sc + off_zero + 8);
+    P.dyn_next = (unsigned*)(sc + off_zero + 32);
+    P.dyn_lock = P.dyn_next + T;
+    P.help_slots = P.dyn_lock + T;
+    P.help_mask = help_cap - 1;
+    P.dyn_found = (unsigned*)(sc + off_dfound);
+    const uint64_t lanes = (uint64_t)plan0.resident_tiles;
+    P.dyn_k0 = T >= lanes ? 0u : (unsigned)((lanes + T - 1) / T - 1);
+    if (P.dyn_k0 > 7) P.dyn_k0 = 7;
+    CUDA_TRY(cudaMemsetAsync(sc + off_zero, 0, 32 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned), s));
+    CUDA_TRY(cudaMemsetAsync(P.dyn_found, 0xff, T * sizeof(unsigned), s));
+    if (d_evals) CUDA_TRY(cudaMemsetAsync(d_evals, 0, T * sizeof(int32_t), s));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), s));
+    if (use_found) {
+      P.found = (unsigned long long*)(sc + off_found);
+      CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
+    }
+  }
+  if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, (P.has_prismatic || P.weighted) ? 1 : 0, rows, plan.blocks, s));
   else CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
   if (per_attempt_records && d_best_record) {  // selection pass over the per-attempt records -> one packed record
     SelectParams S{};
@@ -368,7 +452,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     S.cand_status = P.cand_status; S.cand_evals = P.cand_evals;
     S.tol_f = cfg->tol_f; S.tol_df_user = cfg->tol_df; S.tol_dx = cfg->tol_dx;
     S.record_out = d_best_record;
-    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
+    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? sc + off_part : nullptr, s));
   }
   if (!direct) {
     SelectParams S{};
@@ -379,85 +463,9 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     S.q_out = d_q; S.f_out = d_f; S.status_out = d_status;
     S.restart_out = (unsigned long long*)d_restart;  // optional
     S.evals_out = d_evals;                            // optional
-    if (d_tlist) { S.tlist = d_tlist; S.only_success = 1; S.add_evals = 1; }
-    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? scratch + off_part : nullptr, s));
+    CUDA_TRY(optik_launch_select(&S, slices, slices > 1 ? sc + off_part : nullptr, s));
   }
-  CUDA_TRY(cudaFreeAsync(scratch, s));
   return OPTIK_OK;
-}
-
-// Speed-mode batches in PHASES.  One launch with every target's restarts in sequence ends with the few targets that
-// need 10-25 attempts (a geometric tail), and spreading restarts over parallel chunks from the start wastes attempts
-// on targets whose first seed converges.  Phase 0 runs restarts [0, K0) of every target in order; each later phase
-// compacts the still-unsolved targets on the device, reads their count (the one host sync per phase: it sizes the
-// next launch) and runs their next restarts -- in order while they still fill the GPU, one attempt per parallel chunk
-// with the `found` early exit (lib.rs:382-384) once they do not.  Per target the result is unchanged: the
-// lowest-index converged restart (lib.rs:409-412).
-// Plan (swept on B200 over K0, K, fill factor and one-attempt-per-chunk vs chained chunks): 3 restarts in order per phase while the unsolved targets fill the GPU
-// twice over; afterwards ONE attempt per chunk and as many chunks per target as fill it twice (no chains at all).
-// Panda, 32 restarts: 65 536 targets 3.05 -> 1.51 ms, 262 144 targets 5.28 -> 3.56 ms, 1 Mi targets 10.9 -> 10.5 ms.
-constexpr uint64_t PHASE_K0 = 3, PHASE_K = 3, PHASE_FILL = 2;
-
-bool phased_applies(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o, uint64_t T, uint64_t R,
-                    bool per_attempt_records) {
-  if (cfg->solution_mode != OPTIK_MODE_SPEED || per_attempt_records || (o && o->chunks) || R <= PHASE_K0) return false;
-  if (T > 0xffffffffull) return false;
-  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
-  if (!tile) return false;
-  return T * 4 >= (uint64_t)make_plan(r, tile, 0, ~0ull).resident_tiles;
-}
-
-int solve_device_phased(const optik_robot* r, const optik_solver_config* cfg, const optik_gpu_batch_opts* o,
-                        const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
-                        double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
-                        unsigned long long max_ns, cudaStream_t s) {
-  const auto t_begin = std::chrono::steady_clock::now();
-  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
-  const uint64_t resident = (uint64_t)make_plan(r, tile, 0, ~0ull).resident_tiles;
-  // the evaluation count is needed across phases even when the caller does not ask for it
-  char* aux = nullptr;
-  const size_t aux_bytes = ((T * 4 + 255) & ~size_t(255)) + 256 + (d_evals ? 0 : ((T * 4 + 255) & ~size_t(255)));
-  CUDA_TRY(cudaMallocAsync((void**)&aux, aux_bytes, s));
-  unsigned* d_list = (unsigned*)aux;
-  unsigned* d_count = (unsigned*)(aux + ((T * 4 + 255) & ~size_t(255)));
-  int32_t* evals = d_evals ? d_evals : (int32_t*)(aux + ((T * 4 + 255) & ~size_t(255)) + 256);
-  auto remaining_ns = [&]() -> long long {  // max_time bounds the whole call (lib.rs:260-264)
-    if (!max_ns) return 0;
-    const long long used = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count();
-    return (long long)max_ns - used;
-  };
-  int rc = solve_device(r, cfg, o, d_targets, d_x0, T, r_begin, PHASE_K0, d_q, d_f, d_status, d_restart, evals, d_counters,
-                        max_ns, false, s, nullptr, nullptr, 1);  // one chunk: restarts strictly in order, nothing speculative
-  uint64_t done = PHASE_K0;
-  while (!rc && done < R) {
-    if (cudaMemsetAsync(d_count, 0, sizeof(unsigned), s) != cudaSuccess) { rc = fail(OPTIK_ERR_CUDA, "cudaMemsetAsync failed"); break; }
-    rc = optik_launch_compact_unsolved(d_status, T, cfg->tol_f, cfg->tol_df, cfg->tol_dx, d_list, d_count, s);
-    if (rc) { rc = fail(OPTIK_ERR_CUDA, "compact_unsolved launch failed"); break; }
-    unsigned count = 0;
-    if (cudaMemcpyAsync(&count, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(OPTIK_ERR_CUDA, "phase count readback failed"); break; }
-    if (count == 0) break;
-    unsigned long long ns = 0;
-    if (max_ns) {
-      const long long left = remaining_ns();
-      if (left <= 0) break;
-      ns = (unsigned long long)left;
-    }
-    // while the unsolved targets still fill the GPU twice over: a few more restarts each, in order; afterwards all
-    // remaining restarts, spread over parallel chunks by solve_device's own rule
-    uint64_t k, chunks;
-    if (count >= PHASE_FILL * resident && R - done > PHASE_K) { k = PHASE_K; chunks = 1; }
-    else {  // one attempt per chunk, as many chunks as fill the GPU
-      chunks = (PHASE_FILL * resident + count - 1) / count;
-      if (chunks > R - done) chunks = R - done;
-      k = chunks;
-    }
-    rc = solve_device(r, cfg, o, d_targets, d_x0, count, r_begin + done, k, d_q, d_f, d_status, d_restart, evals, d_counters,
-                      ns, false, s, nullptr, d_list, chunks);
-    done += k;
-  }
-  cudaFreeAsync(aux, s);
-  return rc;
 }
 
 int check_seeds_host(const optik_robot* r, const double* x0, uint64_t T) {  // lib.rs:251-254
@@ -480,7 +488,7 @@ int check_seeds_host(const optik_robot* r, const double* x0, uint64_t T) {  // l
 extern "C" {
 
 const char* optik_last_error(void) { return g_last_error.c_str(); }
-void optik_set_urdf_correct_fold(int on) { g_urdf_correct_fold = on != 0; }
+void optik_set_urdf_correct_fold(int on) { g_urdf_correct_fold.store(on != 0); }
 
 optik_robot* optik_robot_try_from_urdf_str(const char* urdf, const char* base_link, const char* ee_link) {
   return try_from_urdf_str(urdf, base_link, ee_link);
@@ -542,6 +550,7 @@ int optik_robot_set_device(optik_robot* robot, int device) {
 }
 int optik_status_is_success(const optik_solver_config* c, int st) {
   if (!c) return 0;
+  st &= OPTIK_STATUS_CODE_MASK;
   return (c->tol_f >= 0.0 && st == OPTIK_STATUS_STOPVAL) || (c->tol_df >= 0.0 && st == OPTIK_STATUS_FTOL) ||
          (c->tol_dx >= 0.0 && st == OPTIK_STATUS_XTOL);
 }
@@ -576,6 +585,49 @@ int optik_gpu_select_records(const optik_robot* robot, const double* records, ui
   if (!robot || !records || !best_record_out || count == 0) return fail(OPTIK_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(robot->device));
   CUDA_TRY(optik_launch_select_records(records, count, robot->n, best_record_out, stream));
+  return OPTIK_OK;
+}
+
+int optik_gpu_restart_seeds(const optik_robot* robot, uint64_t restart_begin, uint64_t count, int memory, double* seeds_out,
+                            void* stream) {
+  if (!robot || !seeds_out) return fail(OPTIK_ERR_INVALID, "null argument");
+  if (restart_begin == 0 && count) return fail(OPTIK_ERR_INVALID, "restart 0 is the caller's seed; restart_begin must be >= 1");
+  if (count == 0) return OPTIK_OK;
+  {
+    std::lock_guard<std::mutex> lk(robot->mu);
+    if (int rc = robot->ensure_gpu()) return rc;
+  }
+  CUDA_TRY(cudaSetDevice(robot->device));
+  if (robot->n > 8) return fail(OPTIK_ERR_UNSUPPORTED, "seed tables are built for num_positions <= 8");
+  const int n = robot->n;
+  if (memory == 1) {
+    CUDA_TRY(optik_launch_seed_table((const double*)robot->chain_dev.p, n, (const uint32_t*)robot->key_dev.p, restart_begin,
+                                     count, seeds_out, stream));
+    return OPTIK_OK;
+  }
+  std::unique_lock<std::mutex> lk(robot->mu, std::defer_lock);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!s) { lk.lock(); s = robot->stream; }
+  StreamBuf buf;
+  CUDA_TRY(buf.alloc(robot, count * n * sizeof(double), s));
+  CUDA_TRY(optik_launch_seed_table((const double*)robot->chain_dev.p, n, (const uint32_t*)robot->key_dev.p, restart_begin,
+                                   count, (double*)buf.p, s));
+  CUDA_TRY(cudaMemcpyAsync(seeds_out, buf.p, count * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return OPTIK_OK;
+}
+
+int optik_gpu_chacha8_block(const optik_robot* robot, const uint32_t* key8, uint64_t stream_id, uint32_t* words16_out) {
+  if (!robot || !key8 || !words16_out) return fail(OPTIK_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(robot->mu);
+  if (int rc = robot->ensure_gpu()) return rc;
+  CUDA_TRY(cudaSetDevice(robot->device));
+  StreamBuf buf;
+  CUDA_TRY(buf.alloc(robot, 256, robot->stream));
+  CUDA_TRY(cudaMemcpyAsync(buf.p, key8, 32, cudaMemcpyHostToDevice, robot->stream));
+  CUDA_TRY(optik_launch_chacha8_kat((const uint32_t*)buf.p, stream_id, (uint32_t*)(buf.p + 128), robot->stream));
+  CUDA_TRY(cudaMemcpyAsync(words16_out, buf.p + 128, 64, cudaMemcpyDeviceToHost, robot->stream));
+  CUDA_TRY(cudaStreamSynchronize(robot->stream));
   return OPTIK_OK;
 }
 
@@ -654,8 +706,9 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
   auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
   const size_t o_q = carve(B * n * 8), o_t = targets ? carve(nt * 64) : 0, o_ee = ee_out ? carve(B * 64) : 0,
                o_j = jac_out ? carve(B * 6 * n * 8) : 0, o_f = f_out ? carve(B * 8) : 0, o_g = grad_out ? carve(B * n * 8) : 0;
-  char* d = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  StreamBuf buf;
+  CUDA_TRY(buf.alloc(robot, bytes, s));
+  char* d = buf.p;
   CUDA_TRY(cudaMemcpyAsync(d + o_q, q, B * n * 8, cudaMemcpyHostToDevice, s));
   if (targets) CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, nt * 64, cudaMemcpyHostToDevice, s));
   P.q = (double*)(d + o_q); P.targets = targets ? (double*)(d + o_t) : nullptr;
@@ -666,7 +719,6 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
   if (jac_out) CUDA_TRY(cudaMemcpyAsync(jac_out, d + o_j, B * 6 * n * 8, cudaMemcpyDeviceToHost, s));
   if (f_out) CUDA_TRY(cudaMemcpyAsync(f_out, d + o_f, B * 8, cudaMemcpyDeviceToHost, s));
   if (grad_out) CUDA_TRY(cudaMemcpyAsync(grad_out, d + o_g, B * n * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaFreeAsync(d, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return OPTIK_OK;
 }
@@ -700,34 +752,44 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   if (T == 0) return OPTIK_OK;
   uint64_t R = opts ? opts->restarts : 0;
   if (R == 0) {
-    if (config->max_restarts == 0 || config->max_restarts > 0xffffffffull)
-      return fail(OPTIK_ERR_INVALID, "batched ik needs a finite restart budget (opts.restarts or config.max_restarts)");
-    R = config->max_restarts;
+    // the reference's default budget (config.rs:52-65): no restart limit, max_time bounds the call (lib.rs:260-277)
+    if (config->max_restarts == 0 || config->max_restarts > UNBOUNDED_RESTARTS) {
+      if (!(config->max_time > 0.0) || per_attempt)
+        return fail(OPTIK_ERR_INVALID, "no time or restart limit applied -- solver would run forever");
+      R = UNBOUNDED_RESTARTS;
+    } else R = config->max_restarts;
   }
   const uint64_t r_begin = opts ? opts->restart_begin : 0;
   const int memory = opts ? opts->memory : 0;
   const bool async = opts && (opts->flags & OPTIK_BATCH_ASYNC);
   if (async && (memory == 1 || !stream))
     return fail(OPTIK_ERR_INVALID, "OPTIK_BATCH_ASYNC is for host-memory calls on a caller-provided stream");
-  std::unique_lock<std::mutex> lk(robot->mu);
-  if (int rc = robot->ensure_gpu()) return rc;
+  {
+    std::lock_guard<std::mutex> lk(robot->mu);
+    if (int rc = robot->ensure_gpu()) return rc;
+  }
+  // from here on only immutable robot state is read: calls from several threads (or on several streams) overlap
   CUDA_TRY(cudaSetDevice(robot->device));
-  cudaStream_t s = (memory == 1) ? (cudaStream_t)stream : (stream ? (cudaStream_t)stream : robot->stream);
-  if (async) lk.unlock();  // own stream, stream-ordered scratch: nothing of the robot is mutated
   const int n = robot->n;
   const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(config->max_time * 1e9) : 0ull;
   const uint64_t NO = per_attempt ? R : T;  // number of output records
   if (memory == 1) {
-    lk.unlock();
-    // seeds outside the limits cannot be checked without a sync; they are clamped by the kernel (documented)
-    if (opts && (opts->flags & OPTIK_BATCH_PHASED) && phased_applies(robot, config, opts, T, R, per_attempt))
-      return solve_device_phased(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
-                                 opts->restart_out, opts->evals_out, opts->counters, max_ns, s);
-    return solve_device(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
-                        opts ? opts->restart_out : nullptr, per_attempt ? evals_all : (opts ? opts->evals_out : nullptr),
-                        opts ? opts->counters : nullptr, max_ns, per_attempt, s, opts ? opts->best_record_out : nullptr);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = solve_device(robot, config, opts, targets, x0, T, r_begin, R, q_out, cost_out, status_out,
+                          opts ? opts->restart_out : nullptr, per_attempt ? evals_all : (opts ? opts->evals_out : nullptr),
+                          opts ? opts->counters : nullptr, max_ns, per_attempt, s, opts ? opts->best_record_out : nullptr);
+    if (rc) return rc;
+    // the reference panics on a seed outside the limits (lib.rs:251-254); device seeds cannot be checked without a
+    // sync, so they are clamped and the target's status carries OPTIK_STATUS_FLAG_SEED_CLAMPED
+    if (r_begin == 0)
+      CUDA_TRY(optik_launch_flag_clamped((const double*)robot->chain_dev.p, n, x0, T, status_out, 1, s));
+    return OPTIK_OK;
   }
   if (int rc = check_seeds_host(robot, x0, T)) return rc;
+  // host-memory calls without a stream of their own serialise on the robot's stream
+  std::unique_lock<std::mutex> lk(robot->mu, std::defer_lock);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!s) { lk.lock(); s = robot->stream; }
   size_t bytes = 0;
   auto carve = [&](size_t b) { size_t off = bytes; bytes += (b + 255) & ~size_t(255); return off; };
   const bool want_rs = opts && opts->restart_out, want_cnt = opts && opts->counters;
@@ -737,24 +799,17 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   const size_t o_t = carve(T * 64), o_x = carve(T * n * 8), o_q = carve(NO * n * 8), o_f = carve(NO * 8),
                o_s = carve(NO * 4), o_r = want_rs ? carve(NR * 8) : 0, o_e = evals_host ? carve(NO * 4) : 0,
                o_c = want_cnt ? carve(24) : 0, o_br = want_best ? carve((OPTIK_RECORD_HEAD + n) * 8) : 0;
-  char* d = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  StreamBuf buf;
+  CUDA_TRY(buf.alloc(robot, bytes, s));
+  char* d = buf.p;
   CUDA_TRY(cudaMemcpyAsync(d + o_t, targets, T * 64, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d + o_x, x0, T * n * 8, cudaMemcpyHostToDevice, s));
   if (want_cnt) CUDA_TRY(cudaMemsetAsync(d + o_c, 0, 24, s));
-  // host-memory calls synchronise anyway: Speed-mode batches run in phases unless the caller enqueues only (async)
-  const bool phased = !async && !(opts && (opts->flags & OPTIK_BATCH_SINGLE_LAUNCH)) &&
-                      phased_applies(robot, config, opts, T, R, per_attempt);
-  int rc = phased
-               ? solve_device_phased(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R,
-                                     (double*)(d + o_q), (double*)(d + o_f), (int32_t*)(d + o_s),
-                                     want_rs ? (uint64_t*)(d + o_r) : nullptr, evals_host ? (int32_t*)(d + o_e) : nullptr,
-                                     want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns, s)
-               : solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
-                              (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
-                              evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
-                              per_attempt, s, want_best ? (double*)(d + o_br) : nullptr);
-  if (rc) { cudaFreeAsync(d, s); return rc; }
+  if (int rc = solve_device(robot, config, opts, (double*)(d + o_t), (double*)(d + o_x), T, r_begin, R, (double*)(d + o_q),
+                            (double*)(d + o_f), (int32_t*)(d + o_s), want_rs ? (uint64_t*)(d + o_r) : nullptr,
+                            evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
+                            per_attempt, s, want_best ? (double*)(d + o_br) : nullptr))
+    return rc;
   CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, NO * 4, cudaMemcpyDeviceToHost, s));
@@ -764,7 +819,6 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
   if (evals_host) CUDA_TRY(cudaMemcpyAsync(evals_host, d + o_e, NO * 4, cudaMemcpyDeviceToHost, s));
   uint64_t cnt[3] = {0, 0, 0};
   if (want_cnt) CUDA_TRY(cudaMemcpyAsync(async ? opts->counters : cnt, d + o_c, 24, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaFreeAsync(d, s));
   if (async) return OPTIK_OK;  // the caller waits with optik_gpu_stream_sync(stream)
   CUDA_TRY(cudaStreamSynchronize(s));
   if (want_cnt) for (int i = 0; i < 3; i++) opts->counters[i] += cnt[i];
@@ -789,15 +843,16 @@ int optik_gpu_ik_attempts(const optik_robot* robot, const optik_solver_config* c
 // Returns 1 and fills q_out/cost_out when a restart converged, 0 for "no solution" (== None), <0 = -(error code).
 static int ik_single(const optik_robot* robot, const optik_solver_config* config, const double* tgt8, const double* x0,
                      const double* ee_offset, double* q_out, double* cost_out) {
-  const auto t_begin = std::chrono::steady_clock::now();
   const int n = robot->n;
   if (int rc = check_seeds_host(robot, x0, 1)) return -rc;
   std::lock_guard<std::mutex> lk(robot->mu);
   if (int rc = robot->ensure_gpu()) return -rc;
   if (cudaSetDevice(robot->device) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaSetDevice failed");
+  // max_time (lib.rs:260-264) runs from here: the one-time device initialisation of a fresh Robot is not solve time
+  const auto t_begin = std::chrono::steady_clock::now();
   cudaStream_t s = robot->stream;
   const int tile = choose_tile(n, 0, false);  // single target: the low-latency tile layout
-  const Plan plan = make_plan(robot, tile, 0, ~0ull);
+  const Plan plan = make_plan(robot, tile, 2, 0, ~0ull);
   const uint64_t wave = (uint64_t)plan.resident_tiles;                                    // restarts per launch
   const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
   const size_t o_t = 0, o_x = 64, o_q = o_x + ((n * 8 + 255) & ~255), o_f = o_q + ((n * 8 + 255) & ~255), o_s = o_f + 256,
@@ -828,7 +883,10 @@ static int ik_single(const optik_robot* robot, const optik_solver_config* config
     if (config->max_time > 0.0) {
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
       remaining = config->max_time - el;
-      if (remaining <= 0) break;
+      if (remaining <= 0) {
+        if (done > 0) break;
+        remaining = 1e-6;  // at least one wave runs (restart 0 is evaluated once before its deadline check)
+      }
     }
     const uint64_t R = (max_restarts - done) < wave ? (max_restarts - done) : wave;
     const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(remaining * 1e9) + 1 : 0ull;
@@ -913,8 +971,9 @@ extern "C" int optik_gpu_diff_ik_batch(const optik_robot* robot, const double* x
   const uint64_t nV = shared_V ? 6 : 6 * B, nm = shared_vmax ? (uint64_t)n : B * n;
   const size_t o_x = carve(B * n * 8), o_V = carve(nV * 8), o_m = carve(nm * 8), o_a = carve(B * 8), o_v = carve(B * n * 8),
                o_s = carve(B * 4);
-  char* d = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&d, bytes, s));
+  StreamBuf buf;
+  CUDA_TRY(buf.alloc(robot, bytes, s));
+  char* d = buf.p;
   CUDA_TRY(cudaMemcpyAsync(d + o_x, x0, B * n * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d + o_V, V_WE, nV * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d + o_m, v_max, nm * 8, cudaMemcpyHostToDevice, s));
@@ -924,7 +983,6 @@ extern "C" int optik_gpu_diff_ik_batch(const optik_robot* robot, const double* x
   CUDA_TRY(cudaMemcpyAsync(alpha_out, d + o_a, B * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(v_out, d + o_v, B * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, B * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaFreeAsync(d, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return OPTIK_OK;
 }

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
           job = __shfl_sync(tile_mask, next, 0, TILE);
           if (job >= njobs) { done = true; break; }
           tgt_id = job / P.C;
-          src_id = P.tlist ? (unsigned long long)P.tlist[tgt_id] : tgt_id;  // row of targets / x0 (phased batches)
+          src_id = tgt_id;
           r_idx = P.r_begin + job % P.C;
           x0 = (lane < n) ? P.x0[src_id * n + lane] : 0.0;
           if (lane == 0) {  // FK in the target's frame: O_0 <- T_tgt^-1 * origin_0
@@ -404,11 +404,8 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     return;
   }
   const unsigned long long win = w.idx;
-  // phased batches: results are scattered to the target's row, only a converged winner replaces the record the
-  // earlier phases left there, evaluations add up
-  const unsigned long long ot = P.tlist ? (unsigned long long)P.tlist[t] : t;
-  const bool write = !P.only_success || w.has > 0;
-  if (P.q_out && write)
+  const unsigned long long ot = t;
+  if (P.q_out)
     for (int j = threadIdx.x; j < P.n; j += blockDim.x) P.q_out[ot * P.n + j] = P.cand_q[win * P.n + j];
   if (P.record_out) {
     double* rec = P.record_out + ot * (8 + P.n);
@@ -424,50 +421,11 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Sel
     }
   }
   if (threadIdx.x == 0 && P.f_out) {
-    if (write) {
-      P.f_out[ot] = P.cand_f[win];
-      if (P.restart_out) P.restart_out[ot] = P.cand_restart[win];
-      P.status_out[ot] = P.cand_status[win];
-    }
-    if (P.evals_out) P.evals_out[ot] = (P.add_evals ? P.evals_out[ot] : 0) + w.evals;
+    P.f_out[ot] = P.cand_f[win];
+    if (P.restart_out) P.restart_out[ot] = P.cand_restart[win];
+    P.status_out[ot] = P.cand_status[win];
+    if (P.evals_out) P.evals_out[ot] = w.evals;
   }
-}
-
-// Phased batches with ONE chunk per target: the candidate record of job t goes to row tlist[t] if it converged;
-// evaluations add up.  (select_kernel spends a 256-thread block per target, which is wasteful for a single candidate.)
-__global__ void scatter_kernel(const __grid_constant__ SelectParams P) {
-  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P.T) return;
-  const unsigned long long ot = P.tlist ? (unsigned long long)P.tlist[t] : t;
-  const int st = P.cand_status[t];
-  const bool has = (P.tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (P.tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
-                   (P.tol_dx >= 0.0 && st == OPTIK_ST_XTOL);
-  if (!P.only_success || has) {
-    for (int j = 0; j < P.n; j++) P.q_out[ot * P.n + j] = P.cand_q[t * P.n + j];
-    P.f_out[ot] = P.cand_f[t];
-    if (P.restart_out) P.restart_out[ot] = P.cand_restart[t];
-    P.status_out[ot] = st;
-  }
-  if (P.evals_out) P.evals_out[ot] = (P.add_evals ? P.evals_out[ot] : 0) + P.cand_evals[t];
-}
-
-// Phased Speed-mode batches: indices of the targets whose recorded status is not a success (unordered)
-__global__ void compact_unsolved_kernel(const int* __restrict__ status, unsigned long long T, double tol_f, double tol_df_user,
-                                        double tol_dx, unsigned* __restrict__ list, unsigned* __restrict__ count) {
-  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool unsolved = false;
-  if (t < T) {
-    const int st = status[t];
-    unsolved = !((tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
-                 (tol_dx >= 0.0 && st == OPTIK_ST_XTOL));
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, unsolved);
-  if (m == 0u) return;
-  const int lane = threadIdx.x & 31;
-  unsigned base = 0;
-  if (lane == (__ffs(m) - 1)) base = atomicAdd(count, (unsigned)__popc(m));  // one atomic per warp
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (unsolved) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)t;
 }
 
 }  // namespace optik
@@ -495,6 +453,27 @@ __global__ void select_records_kernel(const double* __restrict__ rec, unsigned c
 }
 }  // namespace optik
 
+namespace optik {
+// Device-pointer calls cannot reject a seed outside the joint limits (the reference panics, lib.rs:251-254) without a
+// host sync: the kernels clamp it, and this pass marks the target's status (OPTIK_STATUS_FLAG_SEED_CLAMPED = 0x100).
+__global__ void flag_clamped_kernel(const double* __restrict__ chain, int n, const double* __restrict__ x0, unsigned long long T,
+                                    int* __restrict__ status, unsigned long long status_stride) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  bool out = false;
+  for (int j = 0; j < n; j++) {
+    const double q = x0[t * n + j];
+    out |= !(q >= chain[OPTIK_CHAIN_STRIDE * j + 12] && q <= chain[OPTIK_CHAIN_STRIDE * j + 13]);
+  }
+  if (out) status[t * status_stride] |= 0x100;
+}
+}  // namespace optik
+extern "C" int optik_launch_flag_clamped(const double* chain, int n, const double* x0, unsigned long long T, int* status,
+                                         unsigned long long status_stride, void* stream) {
+  optik::flag_clamped_kernel<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chain, n, x0, T, status, status_stride);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ host launchers (called from robot.cpp)
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream) {
   optik::select_records_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rec, count, n, out);
@@ -511,21 +490,11 @@ extern "C" int optik_launch_solve(const SolveParams* p, int tile, int blocks, vo
   }
   return (int)cudaGetLastError();
 }
-extern "C" int optik_launch_compact_unsolved(const int* status, unsigned long long T, double tol_f, double tol_df_user,
-                                             double tol_dx, unsigned* list, unsigned* count, void* stream) {
-  const unsigned blocks = (unsigned)((T + 255) / 256);
-  optik::compact_unsolved_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(status, T, tol_f, tol_df_user, tol_dx, list, count);
-  return (int)cudaGetLastError();
-}
 extern "C" int optik_select_partial_bytes(void) { return (int)sizeof(optik::SelKey); }
 // slices == 1: one launch.  slices > 1: caller provides partial scratch (T*slices*optik_select_partial_bytes()).
 extern "C" int optik_launch_select(const SelectParams* p, unsigned slices, void* partial_scratch, void* stream) {
   SelectParams P = *p;
   P.final_pass = 0; P.partials = 0; P.partial = nullptr; P.partial_out = nullptr;
-  if (P.C == 1 && P.tlist && !P.record_out) {  // one candidate per target: a plain scatter
-    optik::scatter_kernel<<<(unsigned)((P.T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
-    return (int)cudaGetLastError();
-  }
   if (slices <= 1) {
     optik::select_kernel<<<dim3((unsigned)P.T, 1), 256, 0, (cudaStream_t)stream>>>(P);
     return (int)cudaGetLastError();

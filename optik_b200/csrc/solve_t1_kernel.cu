@@ -2,19 +2,29 @@
 //
 // Same path, objective, stop rules, seeds and LM step as solve_kernel.cu (reference: crates/optik/src/lib.rs:297-413,
 // objective.rs:40-110, kinematics.rs:123-196, math.rs:40-203), but the evaluation order is sequential per seed:
-//   * one BACKWARD recursion in the target's frame on the inverse pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip)
-//     yields joint j's body-Jacobian column [t_C x (R_C a_j); R_C a_j] = [R_Bj^T (a_j x p_Bj); R_Bj^T a_j] with one
-//     rotation and one cross product, and the pose error X = C_0^-1  (as eval_kernel)
+//   * one BACKWARD recursion on the inverse pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip) in the BASE frame yields
+//     joint j's body-Jacobian column [t_C x (R_C a_j); R_C a_j] with one rotation and one cross product; the pose error
+//     is X = (C_0 T_tgt)^-1 (objective.rs:48-49), one isometry product after the loop
 //   * on accept the body columns become task columns by two explicit 3x3 matrices (Jlog6 = [[J, C J],[0, J]], 27 fma
 //     per column)
-//   * columns live in a per-thread shared-memory row (128-bit accesses, odd 16-byte row stride => conflict-free);
-//     two rows per thread: the current point's task columns and the trial point's body columns (swapped on accept)
+//   * the current point's task columns live in a per-thread shared-memory row (128-bit accesses, odd 16-byte row stride
+//     => conflict-free); the trial point's body columns in a second shared row (ROWS = 2, two blocks per SM) or in
+//     thread-local memory (ROWS = 1: L1/L2-resident, written once per evaluation, read back only on accept; three
+//     blocks per SM)
 //   * the 6x6 Gram matrix is accumulated joint by joint with fma; the LDL^T solve is thread-private.
-// Why it exists: in the tile layout every lane of a tile repeats the tile-uniform math (log map, LDL^T), so a
-// 7-DOF seed costs ~240 fp64 issue slots per evaluation; here it costs ~60.  The tile kernel remains the
-// low-latency / long-chain layout (and the literal "one warp per seed" configuration); this one is the batch layout.
-// Threads never communicate: no shuffles, no block barriers in the loop; a thread refills itself with the next
-// (target, chunk) job when its attempt ends (flattened state machine), so lanes of a warp stay busy.
+// Restart seeds (lib.rs:360-370) come from a table in HBM written by seed_table_kernel (one ChaCha8 block per restart,
+// all lanes busy) -- a lone lane drawing a block inside this kernel stalls the 31 other lanes of its warp for ~800
+// instructions; the in-kernel draw remains as the fallback for restart indices beyond the table.
+// Scheduling (lib.rs:297-301, 381-387, 393-413): a flattened state machine, every lane runs ONE uniform loop body
+// (evaluate -> stop tests -> step) and takes its next attempt when one ends:
+//   sched 0  static jobs (target, chunk): chunk c runs restarts r_begin+c, +C, ... in order (Quality batches, per-attempt
+//            records, small Speed batches with the `found` early exit)
+//   sched 1  dynamic Speed chains: a lane that takes a target claims its restarts one by one (atomicAdd on next[t]) until
+//            one converges; once every target has been taken, lanes whose chain ended pop HELP TICKETS that failing
+//            chains push and claim restarts of the same target in parallel.  A claimed index always runs unless a LOWER
+//            index has already converged (found[t], lib.rs:308, 382-384), so the per-target answer is the lowest-index
+//            converged restart (lib.rs:409-412 with one thread) regardless of timing; no host round trip, no tail of
+//            unlucky targets.
 #include <cuda_runtime.h>
 
 #include "ik_math.cuh"
@@ -24,18 +34,21 @@
 namespace optik {
 
 constexpr int T1_THREADS = 128;
+constexpr unsigned FULLMASK = 0xffffffffu;
+constexpr unsigned DYN_NONE = 0xffffffffu;
 
 DEV int t1_row_units(int n) { return (3 * n) | 1; }  // 16-byte units per column row, forced odd
 
-// One ChaCha8 block -> the first 8 u64 of stream `stream` (enough for n <= 8 joints)
-DEV void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
+// One ChaCha8 block -> the first 8 u64 of stream `stream` (enough for n <= 8 joints).  Rolled and not inlined: it is the
+// cold path of the solve kernel (restart indices beyond the seed table) and the whole of seed_table_kernel.
+__device__ __noinline__ void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
   uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
                     key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
                     0u, 0u, (uint32_t)stream, (uint32_t)(stream >> 32)};
   uint32_t x[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) x[i] = s[i];
-#pragma unroll 1  // rolled: the block is drawn once per attempt, its code should not crowd the evaluation loop out of the instruction cache
+#pragma unroll 1
   for (int r = 0; r < 4; r++) {
     OPTIK_QR(x[0], x[4], x[8], x[12]) OPTIK_QR(x[1], x[5], x[9], x[13])
     OPTIK_QR(x[2], x[6], x[10], x[14]) OPTIK_QR(x[3], x[7], x[11], x[15])
@@ -47,20 +60,69 @@ DEV void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
     out8[k] = (uint64_t)(x[2 * k] + s[2 * k]) | ((uint64_t)(x[2 * k + 1] + s[2 * k + 1]) << 32);
 }
 
-__global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
+// Restart seeds for indices [r_begin, r_begin + count): seed[i][j] = clamp(uniform(ChaCha8(42).stream(r).u64[j]))
+// (lib.rs:86-91, 360-370).  Index 0 is the caller's seed and is left untouched.  `chain` is the device blob.
+__global__ void __launch_bounds__(128) seed_table_kernel(const double* __restrict__ chain, int n, const uint32_t* __restrict__ key_g,
+                                                         unsigned long long r_begin, unsigned long long count,
+                                                         double* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned long long r = r_begin + i;
+  if (r == 0) return;
+  uint32_t key[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) key[k] = key_g[k];
+  uint64_t u[8];
+  chacha8_block(key, r, u);
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (j < n) {
+      const double* jc = chain + OPTIK_CHAIN_STRIDE * j;
+      out[i * n + j] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
+    }
+}
+
+// Known-answer hook: the raw 16-word ChaCha8 block (counter 0) of `stream` under `key`, as the kernels compute it
+__global__ void chacha8_kat_kernel(const uint32_t* __restrict__ key_g, unsigned long long stream, uint32_t* __restrict__ out16) {
+  uint32_t key[8];
+  for (int k = 0; k < 8; k++) key[k] = key_g[k];
+  uint64_t u[8];
+  chacha8_block(key, stream, u);
+  for (int k = 0; k < 8; k++) { out16[2 * k] = (uint32_t)u[k]; out16[2 * k + 1] = (uint32_t)(u[k] >> 32); }
+  // words 8..15 of the block are not consumed by the solver (n <= 8 joints use 8 u64 = 16 words: all of them)
+}
+
+// ---- help-ticket queue of the dynamic scheduler (hints only: a lost ticket costs parallelism, never correctness)
+DEV void help_push(const SolveParams& P, unsigned t) {
+  const unsigned long long head = *((volatile unsigned long long*)(P.dyn_ctl + 0));
+  const unsigned long long tail = *((volatile unsigned long long*)(P.dyn_ctl + 1));
+  if (tail - head >= (unsigned long long)(P.help_mask >> 1)) return;  // full enough
+  const unsigned long long s = atomicAdd(P.dyn_ctl + 1, 1ull);
+  atomicExch(P.help_slots + (unsigned)(s & P.help_mask), t + 1u);
+}
+DEV unsigned help_pop(const SolveParams& P) {  // -> target or DYN_NONE
+  const unsigned long long head = *((volatile unsigned long long*)(P.dyn_ctl + 0));
+  const unsigned long long tail = *((volatile unsigned long long*)(P.dyn_ctl + 1));
+  if (head >= tail) return DYN_NONE;
+  if (atomicCAS(P.dyn_ctl + 0, head, head + 1ull) != head) return DYN_NONE;  // lost the race; retry next iteration
+  const unsigned v = atomicExch(P.help_slots + (unsigned)(head & P.help_mask), 0u);
+  return v ? v - 1u : DYN_NONE;  // 0: the producer has not stored yet -- drop the hint
+}
+
+template <bool GENERAL, int ROWS>
+__global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) double smem[];
   const int n = P.n;
-  // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[2][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
-  //         qnext[n][T] | per-joint constants origin_q (x) (axis, 0) [n][4]
+  // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[ROWS][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
+  //         per-joint constants origin_q (x) (axis, 0) [n][4]
   double* s_chain = smem;
   double* s_tip = smem + OPTIK_CHAIN_STRIDE * n + 8;
   uint64_t* s_bar = (uint64_t*)(s_tip + 8);
   const int units = t1_row_units(n);
   double2* s_rows = (double2*)(s_tip + 10);
-  double* s_qc = (double*)(s_rows + 2 * T1_THREADS * units);
+  double* s_qc = (double*)(s_rows + ROWS * T1_THREADS * units);
   double* s_qt = s_qc + n * T1_THREADS;
-  double* s_qn = s_qt + n * T1_THREADS;
-  double* s_oa = s_qn + n * T1_THREADS;
+  double* s_oa = s_qt + n * T1_THREADS;
   stage_chain_tma(s_chain, s_bar, P.chain, P.chain_bytes);
   if (threadIdx.x == 0) {  // (fixed tip joint * ee_offset)^-1, once per block
     const se3 tip = se3mul(load_pose8(s_chain + OPTIK_CHAIN_STRIDE * n), load_pose8(P.ee_offset));
@@ -83,175 +145,162 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
   const int tid = threadIdx.x;
   double* qc = s_qc + tid;  // qc[j * T1_THREADS]
   double* qt_ = s_qt + tid;
-  double* qn = s_qn + tid;  // prefetched seed of this thread's next attempt
   double2* const row0 = s_rows + (size_t)tid * units;  // rows[k] = row0 + k * row_stride
   const size_t row_stride = (size_t)T1_THREADS * units;
-  const unsigned long long njobs = P.T * (unsigned long long)P.C;
+  double2 ltrial[ROWS == 1 ? 3 * 8 : 1];  // ROWS == 1: the trial point's body columns (thread-local memory)
+  const unsigned long long njobs = P.sched ? P.T : P.T * (unsigned long long)P.C;
   const bool speed = (P.mode == 2);
+  const bool dyn = (P.sched != 0);
   const unsigned long long t_start = P.max_ns ? globaltimer_ns() : 0ull;
-  constexpr unsigned FULL = 0xffffffffu;
-  const bool prefetch = njobs >= 8ull * T1_THREADS * gridDim.x;
+  const unsigned long long nrest = P.r_end - P.r_begin;
 
-  // ---- per-thread state.  A "job" is one (target, chunk): restarts r_begin+c, +C, ... run in index order.
-  unsigned long long job = 0, tgt_id = 0, src_id = 0, r_idx = 0, nxt_job = 0, nxt_r = 0;
-  bool running = false, job_open = false, best_has = false, rec_any = false, have_next = false, queue_done = false, done = false;
-  se3 O0;  // origin of joint 0 pre-multiplied by T_tgt^-1 (FK in the target's frame)
-  O0.q.x = O0.q.y = O0.q.z = 0; O0.q.w = 1; O0.t = mk3(0, 0, 0);
-  qt O0a = O0.q;  // O0.q (x) (axis_0, 0)
+  // ---- per-thread state.  Static: a "job" is one (target, chunk).  Dynamic: a "chain" on one target.
+  unsigned long long job = 0, tgt_id = 0, src_id = 0, r_idx = 0, r_next = 0;
+  bool running = false, job_open = false, best_has = false, rec_any = false, done = false, fresh_done = false;
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
 
   for (;;) {
-    // ---------------- seed pipeline.  Drawing a restart seed (one ChaCha8 block, ~800 integer instructions) by a lone
-    // lane would cost a full warp issue slot per instruction, so seeds are PREFETCHED: whenever some lane is idle
-    // without a prefetched attempt, every lane lacking one refills in the same pass (lib.rs:360-370 per lane).
-    // With few jobs per thread (prefetch == 0) only idle lanes pull from the QUEUE, so that no lane hoards a job another
-    // could run.
-    if (__any_sync(FULL, !running && !have_next && !queue_done)) {
-      // the next restart of a thread's OWN chunk can always be drawn ahead (nobody else could run it); only pulling
-      // a new job off the queue early is restricted to launches with many jobs per thread
-      const bool own_next = job_open && r_idx + P.C < P.r_end;
-      if (!have_next && !queue_done && (prefetch || !running || own_next)) {
-        bool got = false;
-        if (own_next) {  // next restart of my own chunk
-          nxt_job = job; nxt_r = r_idx + P.C; got = true;
-        } else {
-          nxt_job = atomicAdd(P.queue, 1ull);  // dynamic job queue
-          if (nxt_job >= njobs) queue_done = true;
-          else {
-            const unsigned long long c = (P.C == 1) ? 0ull : (P.T == 1 ? nxt_job : nxt_job % P.C);
-            nxt_r = P.r_begin + c;
-            got = nxt_r < P.r_end;
-            if (!got) {  // chunk without any restart (C > R): empty record, job consumed
-              const unsigned long long t = (P.C == 1) ? nxt_job : (P.T == 1 ? 0ull : nxt_job / P.C);
-              const unsigned long long ts = P.tlist ? (unsigned long long)P.tlist[t] : t;
-              for (int j = 0; j < n; j++) P.cand_q[nxt_job * n + j] = P.x0[ts * n + j];
-              P.cand_f[nxt_job] = 0.0; P.cand_score[nxt_job] = 0.0; P.cand_restart[nxt_job] = nxt_r;
-              P.cand_status[nxt_job] = OPTIK_ST_SKIPPED; P.cand_evals[nxt_job] = 0;
-            }
-          }
-        }
-        if (got) {
-          if (nxt_r != 0) {
-            uint64_t u[8];
-            chacha8_block(P.key, nxt_r, u);
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-              if (j < n) {
-                const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-                qn[j * T1_THREADS] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
-              }
-          } else {
-            const unsigned long long t = (P.C == 1) ? nxt_job : (P.T == 1 ? 0ull : nxt_job / P.C);
-            const unsigned long long ts = P.tlist ? (unsigned long long)P.tlist[t] : t;
-            for (int j = 0; j < n; j++) {
-              const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-              qn[j * T1_THREADS] = fmin(fmax(P.x0[ts * n + j], jc[12]), jc[13]);
-            }
-          }
-          have_next = true;
-        }
-      }
-    }
-    // ---------------- transitions of idle threads: start the prefetched attempt
+    // ---------------- transitions of idle threads: take the next attempt
     if (!running && !done) {
-      if (have_next) {
-        have_next = false;
-        if (!job_open || nxt_job != job) {  // open a new job
-          if (job_open) P.cand_evals[job] = job_evals;
-          job = nxt_job;
-          tgt_id = (P.C == 1) ? job : (P.T == 1 ? 0ull : job / P.C);
-          src_id = P.tlist ? (unsigned long long)P.tlist[tgt_id] : tgt_id;  // row of targets / x0 (phased batches)
-          const se3 tgt = load_pose8(P.targets + 8 * src_id);
-          se3 ti, o0;
-          ti.q = qconj(tgt.q);
-          ti.t = neg3(qrot(ti.q, tgt.t));
-          o0.q.x = s_chain[4]; o0.q.y = s_chain[5]; o0.q.z = s_chain[6]; o0.q.w = s_chain[7];
-          o0.t = mk3(s_chain[0], s_chain[1], s_chain[2]);
-          O0 = se3mul(ti, o0);
-          qt a0;
-          a0.x = s_chain[8]; a0.y = s_chain[9]; a0.z = s_chain[10]; a0.w = 0.0;
-          O0a = qmul(O0.q, a0);
-          best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
-          for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[src_id * n + j];  // record if no attempt runs
-          P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = nxt_r;
-          P.cand_status[job] = OPTIK_ST_SKIPPED;
-          job_open = true;
-        }
-        r_idx = nxt_r;
-        bool skip = false;
-        if (speed && P.found) skip = *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx;
-        if (!skip && P.max_ns) skip = (globaltimer_ns() - t_start) > P.max_ns;
-        if (skip) {  // every later restart of this chunk is skipped too: the job ends
-          P.cand_evals[job] = job_evals;
+      bool got = false;
+      if (!dyn) {
+        for (;;) {
+          if (!job_open) {
+            job = atomicAdd(P.queue, 1ull);  // dynamic job queue
+            if (job >= njobs) { done = true; break; }
+            const unsigned long long c = (P.C == 1) ? 0ull : (P.T == 1 ? job : job % P.C);
+            tgt_id = (P.C == 1) ? job : (P.T == 1 ? 0ull : job / P.C);
+            src_id = tgt_id;
+            r_next = P.r_begin + c;
+            best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
+            for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[src_id * n + j];  // record if no attempt runs
+            P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_next;
+            P.cand_status[job] = OPTIK_ST_SKIPPED;
+            job_open = true;
+          }
+          bool go = r_next < P.r_end;
+          if (go && speed && P.found) go = !(*((volatile unsigned long long*)(P.found + tgt_id)) < r_next);
+          if (go && P.max_ns) go = !((globaltimer_ns() - t_start) > P.max_ns);
+          if (go) { r_idx = r_next; r_next += P.C; got = true; break; }
+          P.cand_evals[job] = job_evals;  // the chunk is finished
           job_open = false;
-        } else {
-          for (int j = 0; j < n; j++) qt_[j * T1_THREADS] = qn[j * T1_THREADS];
-          have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
-          running = true;
         }
-      } else if (queue_done) {
-        if (job_open) { P.cand_evals[job] = job_evals; job_open = false; }
-        done = true;
+      } else {
+        for (int tries = 0; tries < 4; tries++) {  // bounded: stale tickets are retried in the next pass
+          if (job_open) {  // continue my chain: claim the next restart unless a restart already converged
+            bool go = *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE;
+            if (go && P.max_ns) go = !((globaltimer_ns() - t_start) > P.max_ns);
+            if (go) {
+              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + tgt_id, 1u);
+              if (rel < nrest) { r_idx = P.r_begin + rel; got = true; break; }
+            }
+            job_open = false;  // chain over
+            atomicAdd(P.dyn_ctl + 2, ~0ull);
+          }
+          unsigned t = DYN_NONE;
+          if (!fresh_done) {
+            const unsigned long long f = atomicAdd(P.queue, 1ull);
+            if (f < P.T) {  // a fresh target: default record (kept if no attempt ever runs), then -- with fewer targets
+              t = (unsigned)f;  // than resident lanes -- tickets for parallel chains from the start
+              for (int j = 0; j < n; j++) P.cand_q[f * n + j] = P.x0[f * n + j];
+              P.cand_f[f] = 0.0; P.cand_status[f] = OPTIK_ST_SKIPPED;
+              if (P.cand_restart) P.cand_restart[f] = P.r_begin;
+              if (P.dyn_k0) {
+                __threadfence();
+                for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, t);
+              }
+            } else fresh_done = true;
+          }
+          if (t == DYN_NONE && fresh_done) {
+            t = help_pop(P);
+            if (t == DYN_NONE) {
+              if (*((volatile unsigned long long*)(P.dyn_ctl + 2)) == 0ull) done = true;  // no chain anywhere: finished
+              break;  // otherwise poll again in the next pass
+            }
+            if (*((volatile unsigned*)(P.dyn_found + t)) != DYN_NONE) continue;  // stale ticket
+          }
+          if (t == DYN_NONE) continue;
+          tgt_id = src_id = job = t;
+          job_open = true;
+          atomicAdd(P.dyn_ctl + 2, 1ull);
+        }
+      }
+      if (got) {  // restart 0 = the caller's seed, i >= 1 = ChaCha8 stream i (lib.rs:360-370)
+        if (r_idx == 0) {
+          for (int j = 0; j < n; j++) {
+            const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
+            qt_[j * T1_THREADS] = fmin(fmax(P.x0[src_id * n + j], jc[12]), jc[13]);
+          }
+        } else if (r_idx - P.seed_begin < P.seed_count) {
+          const double* sd = P.seed_tab + (r_idx - P.seed_begin) * n;
+          for (int j = 0; j < n; j++) qt_[j * T1_THREADS] = __ldg(sd + j);
+        } else {
+          uint64_t u[8];
+          chacha8_block(P.key, r_idx, u);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < n) {
+              const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
+              qt_[j * T1_THREADS] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
+            }
+        }
+        have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
+        running = true;
       }
     }
-    if (__all_sync(FULL, done)) break;
+    if (__all_sync(FULLMASK, done)) break;
+    if (!__any_sync(FULLMASK, running)) { __nanosleep(400); continue; }  // dynamic mode: every lane is polling for tickets
     if (!running) continue;
 
-    // ---------------- evaluate the trial point: backward recursion in the target's frame
-    double2* trow = row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
+    // ---------------- evaluate the trial point: backward recursion on the inverse pose, base frame
+    double2* trow = (ROWS == 1) ? ltrial : row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
     se3 Ci = load_pose8(s_tip);  // C_n = tip^-1
 #pragma unroll 1
     for (int j = n - 1; j >= 0; j--) {
       const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
-      const double2 c1 = jc[1], c4 = jc[4], c5 = jc[5];
-      const int type = (int)c1.y;
+      const double2 c0 = jc[0], c1 = jc[1], c2 = jc[2], c3 = jc[3], c4 = jc[4], c5 = jc[5];
+      const double2 a0 = ((const double2*)s_oa)[2 * j], a1 = ((const double2*)s_oa)[2 * j + 1];
+      const bool pris = GENERAL && ((int)c1.y != 0);
       const v3 ax = mk3(c4.x, c4.y, c5.x);
       v3 lin, ang = qrot(Ci.q, ax);
-      if (type == 0) lin = cross3(Ci.t, ang);
+      if (!pris) lin = cross3(Ci.t, ang);
       else { lin = ang; ang = mk3(0, 0, 0); }
       trow[3 * j + 0] = make_double2(lin.x, lin.y);
       trow[3 * j + 1] = make_double2(lin.z, ang.x);
       trow[3 * j + 2] = make_double2(ang.y, ang.z);
-      se3 O;
-      qt oa;
-      if (j == 0) { O = O0; oa = O0a; }
-      else {
-        const double2 c0 = jc[0], c2 = jc[2], c3 = jc[3];
-        const double2 a0 = ((const double2*)s_oa)[2 * j], a1 = ((const double2*)s_oa)[2 * j + 1];
-        O.t = mk3(c0.x, c0.y, c1.x);
-        O.q.x = c2.x; O.q.y = c2.y; O.q.z = c3.x; O.q.w = c3.y;
-        oa.x = a0.x; oa.y = a0.y; oa.z = a1.x; oa.w = a1.y;
-      }
       const double qj = qt_[j * T1_THREADS];
       qt lq;  // conj(L_j.q)
-      v3 lt = O.t;
-      if (type == 0) {
+      v3 lt = mk3(c0.x, c0.y, c1.x);
+      if (!pris) {
         double s, c;
         dsincos(0.5 * qj, s, c);
-        lq.x = -fma(c, O.q.x, s * oa.x); lq.y = -fma(c, O.q.y, s * oa.y); lq.z = -fma(c, O.q.z, s * oa.z);
-        lq.w = fma(c, O.q.w, s * oa.w);
+        lq.x = -fma(c, c2.x, s * a0.x); lq.y = -fma(c, c2.y, s * a0.y); lq.z = -fma(c, c3.x, s * a1.x);
+        lq.w = fma(c, c3.y, s * a1.y);
       } else {
-        lq = qconj(O.q);
-        lt = add3(O.t, qrot(O.q, scale3(ax, qj)));
+        qt oq;
+        oq.x = c2.x; oq.y = c2.y; oq.z = c3.x; oq.w = c3.y;
+        lq = qconj(oq);
+        lt = add3(lt, qrot(oq, scale3(ax, qj)));
       }
       Ci.q = qmul(Ci.q, lq);
       Ci.t = sub3(Ci.t, qrot(Ci.q, lt));
     }
-    se3 B;  // X = C_0^-1
-    B.q = qconj(Ci.q);
-    B.t = neg3(qrot(B.q, Ci.t));
+    const se3 tgt = load_pose8(P.targets + 8 * src_id);
+    se3 B;  // X = (C_0 T_tgt)^-1
+    {
+      const qt xiq = qmul(Ci.q, tgt.q);
+      const v3 xit = add3(Ci.t, qrot(Ci.q, tgt.t));
+      B.q = qconj(xiq);
+      B.t = neg3(qrot(B.q, xit));
+    }
     ErrCoef ec;
     v3 elin;
     error_terms(B.q, B.t, ec, elin);
     v3 rl = elin, ra = ec.w;
-    qt tq;
-    if (P.weighted) {
-      const double* tp = P.targets + 8 * src_id;
-      tq.x = tp[0]; tq.y = tp[1]; tq.z = tp[2]; tq.w = tp[3];
-      rl = weight3(tq, P.wl, elin); ra = weight3(tq, P.wa, ec.w);
-    }
+    const bool weighted = GENERAL && P.weighted;
+    if (weighted) { rl = weight3(tgt.q, P.wl, elin); ra = weight3(tgt.q, P.wa, ec.w); }
     double rt[6] = {rl.x, rl.y, rl.z, ra.x, ra.y, ra.z};
     const double ft = dot6(rt, rt);
 
@@ -280,62 +329,101 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     }
     if (status == OPTIK_ST_NONE && evals >= P.max_evals) status = OPTIK_ST_ITERCAP;
     if (status == OPTIK_ST_NONE && P.max_ns && (globaltimer_ns() - t_start) > P.max_ns) status = OPTIK_ST_SKIPPED;
-    if (status == OPTIK_ST_NONE && speed && P.found && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx)
-      status = OPTIK_ST_SKIPPED;  // should_exit (lib.rs:308)
+    if (status == OPTIK_ST_NONE && speed) {  // should_exit (lib.rs:308): a LOWER restart index of this target converged
+      if (dyn) {
+        if (*((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
+      } else if (P.found && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
+    }
 
     if (status != OPTIK_ST_NONE) {  // attempt over
       const bool success = (P.tol_f >= 0.0 && status == OPTIK_ST_STOPVAL) ||
                            (P.tol_df_user >= 0.0 && status == OPTIK_ST_FTOL) ||
                            (P.tol_dx >= 0.0 && status == OPTIK_ST_XTOL);  // lib.rs:376-379
-      double score = 0.0;
-      if (success && !speed)  // Quality score ||q - x0||^2 (lib.rs:402-407)
-        for (int j = 0; j < n; j++) {
-          const double d = qt_[j * T1_THREADS] - P.x0[src_id * n + j];
-          score = fma(d, d, score);
+      n_attempts++; n_evals += evals;
+      if (success) n_conv++;
+      if (!dyn) {
+        double score = 0.0;
+        if (success && !speed)  // Quality score ||q - x0||^2 (lib.rs:402-407)
+          for (int j = 0; j < n; j++) {
+            const double d = qt_[j * T1_THREADS] - P.x0[src_id * n + j];
+            score = fma(d, d, score);
+          }
+        job_evals += evals;
+        const bool record = success ? (!best_has || score < best_score) : !rec_any;  // failures: keep the first
+        if (record) {
+          rec_any = true;
+          for (int j = 0; j < n; j++) P.cand_q[job * n + j] = qt_[j * T1_THREADS];
+          P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
         }
-      n_attempts++; n_evals += evals; job_evals += evals;
-      const bool record = success ? (!best_has || score < best_score) : !rec_any;  // failures: keep the first
-      if (record) {
-        rec_any = true;
-        for (int j = 0; j < n; j++) P.cand_q[job * n + j] = qt_[j * T1_THREADS];
-        P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
-      }
-      if (success) {
-        n_conv++;
-        if (record) { best_has = true; best_score = score; }
-        if (speed) {  // first success ends the chunk (lib.rs:381-387, 411)
-          if (P.found) atomicMin(P.found + tgt_id, r_idx);
-          P.cand_evals[job] = job_evals;
-          job_open = false;
-          if (have_next && nxt_job == job) have_next = false;  // the prefetched restart of this chunk is moot
+        if (success) {
+          if (record) { best_has = true; best_score = score; }
+          if (speed) {  // first success ends the chunk (lib.rs:381-387, 411)
+            if (P.found) atomicMin(P.found + tgt_id, r_idx);
+            r_next = P.r_end;
+          }
+        }
+      } else {
+        // dynamic chains: the target's record is the lowest-index converged attempt, or the first attempt's failure.
+        // Writers serialise on a per-target lock and re-check found[t] under it, so the row is never torn.
+        const unsigned rel = (unsigned)(r_idx - P.r_begin);
+        bool write = false;
+        if (success) write = atomicMin(P.dyn_found + tgt_id, rel) > rel;
+        else write = (rel == 0u) && status != OPTIK_ST_SKIPPED;
+        if (P.cand_evals) atomicAdd(P.cand_evals + tgt_id, evals);
+        if (write) {
+          bool locked = false;
+          while (!locked) {
+            if (atomicCAS(P.dyn_lock + tgt_id, 0u, 1u) == 0u) {
+              const unsigned fnow = *((volatile unsigned*)(P.dyn_found + tgt_id));
+              if (success ? fnow == rel : fnow == DYN_NONE) {
+                for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
+                P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
+                if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
+              }
+              __threadfence();
+              atomicExch(P.dyn_lock + tgt_id, 0u);
+              locked = true;
+            }
+          }
+        }
+        // a failing chain invites helpers once every target has been taken (they claim this target's next restarts in
+        // parallel); how many depends on how many lanes have nothing else to do
+        if (!success && status != OPTIK_ST_SKIPPED && *((volatile unsigned long long*)P.queue) >= P.T) {
+          const unsigned long long live = *((volatile unsigned long long*)(P.dyn_ctl + 2));
+          const unsigned long long lanes = (unsigned long long)gridDim.x * T1_THREADS;
+          unsigned h = 1;
+          if (live * 2 < lanes) h = 2;
+          if (live * 4 < lanes) h = 3;
+          for (unsigned k = 0; k < h; k++) help_push(P, (unsigned)tgt_id);
         }
       }
       running = false;
       continue;
     }
 
-    if (accept) {  // current point <- trial point; body columns -> task columns, in place
+    if (accept) {  // current point <- trial point; body columns -> task columns
       for (int j = 0; j < n; j++) qc[j * T1_THREADS] = qt_[j * T1_THREADS];
       fc = ft; have_cur = 1;
 #pragma unroll
       for (int i = 0; i < 6; i++) rc[i] = rt[i];
       double Jm[9], CJ[9];
       task_mats(ec, Jm, CJ);
+      double2* wrow = (ROWS == 1) ? row0 : trow;  // ROWS == 2: converted in place, then the rows swap
 #pragma unroll 1
       for (int j = 0; j < n; j++) {
         const double2 a0 = trow[3 * j + 0], a1 = trow[3 * j + 1], a2 = trow[3 * j + 2];
         v3 top, bot;
         task_col_m(Jm, CJ, mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), top, bot);
-        if (P.weighted) { top = weight3(tq, P.wl, top); bot = weight3(tq, P.wa, bot); }
-        trow[3 * j + 0] = make_double2(top.x, top.y);
-        trow[3 * j + 1] = make_double2(top.z, bot.x);
-        trow[3 * j + 2] = make_double2(bot.y, bot.z);
+        if (weighted) { top = weight3(tgt.q, P.wl, top); bot = weight3(tgt.q, P.wa, bot); }
+        wrow[3 * j + 0] = make_double2(top.x, top.y);
+        wrow[3 * j + 1] = make_double2(top.z, bot.x);
+        wrow[3 * j + 2] = make_double2(bot.y, bot.z);
       }
-      cur ^= 1;
+      if (ROWS == 2) cur ^= 1;
     }
 
     // ---------------- LM step from the current point: y = (Jm Jm^T + lambda I)^-1 r ; dq = -Jm^T y ; project on bounds
-    const double2* crow = row0 + (size_t)cur * row_stride;
+    const double2* crow = (ROWS == 1) ? row0 : row0 + (size_t)cur * row_stride;
     double Ap[21];
 #pragma unroll
     for (int e = 0; e < 21; e++) Ap[e] = 0.0;
@@ -376,7 +464,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
     unsigned a = n_attempts, e = n_evals, c = n_conv;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o); e += __shfl_xor_sync(0xffffffffu, e, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+      a += __shfl_xor_sync(FULLMASK, a, o); e += __shfl_xor_sync(FULLMASK, e, o); c += __shfl_xor_sync(FULLMASK, c, o);
     }
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(P.counters + 0, (unsigned long long)a);
@@ -386,23 +474,47 @@ __global__ void __launch_bounds__(T1_THREADS, 2) solve_t1_kernel(const __grid_co
   }
 }
 
-}  // namespace optik
-
-extern "C" int optik_t1_smem_bytes(int n) {
+template <bool GENERAL, int ROWS>
+static int t1_smem_bytes(int n) {
   const size_t units = (size_t)((3 * n) | 1);
-  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * 2 * optik::T1_THREADS * units +
-               sizeof(double) * 3 * n * optik::T1_THREADS + sizeof(double) * 4 * n);
+  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * ROWS * T1_THREADS * units +
+               sizeof(double) * 2 * n * T1_THREADS + sizeof(double) * 4 * n);
 }
-extern "C" int optik_launch_solve_t1(const SolveParams* p, int blocks, void* stream) {
-  const int smem = optik_t1_smem_bytes(p->n);
-  cudaError_t e = cudaFuncSetAttribute(optik::solve_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <bool GENERAL, int ROWS>
+static int t1_launch(const SolveParams* p, int blocks, cudaStream_t s) {
+  const int smem = t1_smem_bytes<GENERAL, ROWS>(p->n);
+  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  optik::solve_t1_kernel<<<blocks, optik::T1_THREADS, smem, (cudaStream_t)stream>>>(*p);
+  solve_t1_kernel<GENERAL, ROWS><<<blocks, T1_THREADS, smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
-extern "C" int optik_solve_t1_occupancy(int n, int* blocks_per_sm) {
-  const int smem = optik_t1_smem_bytes(n);
-  cudaError_t e = cudaFuncSetAttribute(optik::solve_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <bool GENERAL, int ROWS>
+static int t1_occupancy(int n, int* blocks_per_sm) {
+  const int smem = t1_smem_bytes<GENERAL, ROWS>(n);
+  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, optik::solve_t1_kernel, optik::T1_THREADS, smem);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_t1_kernel<GENERAL, ROWS>, T1_THREADS, smem);
+}
+
+}  // namespace optik
+
+// general = the chain has a prismatic joint or the config has non-unit weights; rows = 1 or 2 (see the file header)
+extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows, int blocks, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows == 1) return general ? optik::t1_launch<true, 1>(p, blocks, s) : optik::t1_launch<false, 1>(p, blocks, s);
+  return general ? optik::t1_launch<true, 2>(p, blocks, s) : optik::t1_launch<false, 2>(p, blocks, s);
+}
+extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
+  return rows == 1 ? optik::t1_occupancy<false, 1>(n, blocks_per_sm) : optik::t1_occupancy<false, 2>(n, blocks_per_sm);
+}
+extern "C" int optik_launch_seed_table(const double* chain, int n, const uint32_t* key_dev, unsigned long long r_begin,
+                                       unsigned long long count, double* out, void* stream) {
+  if (count == 0) return 0;
+  const unsigned blocks = (unsigned)((count + 127) / 128);
+  optik::seed_table_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(chain, n, key_dev, r_begin, count, out);
+  return (int)cudaGetLastError();
+}
+extern "C" int optik_launch_chacha8_kat(const uint32_t* key_dev, unsigned long long stream_id, uint32_t* out16_dev, void* stream) {
+  optik::chacha8_kat_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(key_dev, stream_id, out16_dev);
+  return (int)cudaGetLastError();
 }

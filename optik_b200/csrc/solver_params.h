@@ -34,6 +34,11 @@ enum {
 #define OPTIK_LM_STALL_REL 1e-1
 #define OPTIK_LM_STALL_COUNT 2
 
+// thread-per-seed kernel variant used by default: rows of column storage in shared memory (see solve_t1_kernel.cu)
+#ifndef OPTIK_T1_DEFAULT_ROWS
+#define OPTIK_T1_DEFAULT_ROWS 2
+#endif
+
 struct SolveParams {
   // problem
   const double* chain;  // device blob (see above)
@@ -69,7 +74,20 @@ struct SolveParams {
   int* cand_status;                   // status of the recorded attempt
   int* cand_evals;                    // evaluations spent by this chunk (all its attempts)
   unsigned long long* counters;       // [0] attempts run, [1] evaluations, [2] converged attempts (optional)
-  const unsigned* tlist;              // phased batches: target t of THIS launch reads row tlist[t] of targets / x0 (or null)
+  // restart seeds for indices [seed_begin, seed_begin + seed_count) written by seed_table_kernel: [count][n], already
+  // clamped to the limits; indices outside the table are drawn in-kernel (thread-per-seed kernel only)
+  const double* seed_tab;
+  unsigned long long seed_begin, seed_count;
+  // thread-per-seed kernel, sched = 1: dynamic Speed chains (see solve_t1_kernel.cu).  The per-target record goes to
+  // cand_q/f/status/restart[t] directly (cand_evals[t] += evaluations, zeroed by the host; cand_score unused).
+  int sched;
+  unsigned dyn_k0;                    // help tickets pushed when a target is first taken (T < resident lanes)
+  unsigned* dyn_next;                 // [T] next relative restart index to claim            (zeroed)
+  unsigned* dyn_found;                // [T] lowest converged relative restart index so far  (0xffffffff)
+  unsigned* dyn_lock;                 // [T] record lock                                     (zeroed)
+  unsigned long long* dyn_ctl;        // [0] ticket head [1] ticket tail [2] live chains     (zeroed)
+  unsigned* help_slots;               // [help_mask + 1] ticket ring, value = target + 1     (zeroed)
+  unsigned help_mask;
 };
 
 namespace optik { struct SelKey; }
@@ -91,9 +109,6 @@ struct SelectParams {
   int* evals_out;                    // [T] total evaluations spent on the target
   double* record_out;                // [T][8+n] packed candidate record (see optik_b200.h), may be null
   int mode;                          // 1 Quality, 2 Speed (record score)
-  // phased batches: scatter outputs to row tlist[t]; write only converged winners; add to evals_out instead of setting it
-  const unsigned* tlist;
-  int only_success, add_evals;
   // two-level reduction for targets with very many chunks (set by optik_launch_select)
   int final_pass;
   unsigned partials;

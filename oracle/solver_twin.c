@@ -372,17 +372,14 @@ int twin_attempt(const twin_chain* c, const twin_params* P, se3t tgt, const doub
 
 /* ======================= layout 1: thread-per-seed kernel (solve_t1_kernel.cu) =======================
  * Same objective, stop rules and LM step; sequential instead of lane-parallel evaluation order:
- *   - one BACKWARD recursion in the target's frame on the INVERSE pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip):
+ *   - one BACKWARD recursion in the BASE frame on the INVERSE pose C_j = B_j^-1 (B_{j-1} = L_j B_j, B_n = tip):
  *       column of joint j = [ t_C x (R_C a_j) ; R_C a_j ]  ( = [R_Bj^T (a_j x p_Bj) ; R_Bj^T a_j] ),
  *       conj(L_j.q) = conj(cos * origin_q + sin * (origin_q (x) (a_j, 0))),
- *       C.q <- C.q (x) conj(L_j.q),  C.t <- C.t - R_C.q(new) L_j.t ;   X = C_0^-1
+ *       C.q <- C.q (x) conj(L_j.q),  C.t <- C.t - R_C.q(new) L_j.t ;   X = (C_0 T_tgt)^-1   (objective.rs:48-49)
  *   - Gram matrix and score are accumulated joint by joint with fma (no tree). */
 static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, const double* q, double* f, double* r,
                          double body[][6], err_coef* ec) {
   int n = c->n;
-  se3t tgt_inv;
-  tgt_inv.q = qt_conj(tgt.q);
-  tgt_inv.t = v3_neg(qt_rot(tgt_inv.q, tgt.t));
   se3t C; /* tip^-1 */
   C.q = qt_conj(c->tip.q);
   C.t = v3_neg(qt_rot(C.q, c->tip.t));
@@ -397,7 +394,6 @@ static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, co
     }
     se3t O;
     O.q = c->oq[j]; O.t = c->ot[j];
-    if (j == 0) O = se3_mul(tgt_inv, O);
     qt lq; /* conj(L.q) */
     v3 lt = O.t;
     if (c->type[j] == 0) {
@@ -414,8 +410,10 @@ static void twin_eval_t1(const twin_chain* c, const twin_params* P, se3t tgt, co
     C.q = qt_mul(C.q, lq);
     C.t = v3_sub(C.t, qt_rot(C.q, lt));
   }
-  qt xq = qt_conj(C.q);
-  v3 xt = v3_neg(qt_rot(xq, C.t));
+  qt xiq = qt_mul(C.q, tgt.q); /* X^-1 = C_0 T_tgt */
+  v3 xit = v3_add(C.t, qt_rot(C.q, tgt.t));
+  qt xq = qt_conj(xiq);
+  v3 xt = v3_neg(qt_rot(xq, xit));
   v3 elin;
   error_terms(xq, xt, ec, &elin);
   v3 rl = elin, ra = ec->w;

@@ -664,22 +664,27 @@ def test_cpp_consumer_end_to_end(name, tmp_path):
     assert dik >= solved - 2  # a solution may sit at a singular pose (diff_ik -> None)
 
 
-@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8)])
-def test_phased_speed_batches_equal_single_launch(name, T, R):
-    """OPTIK_BATCH_PHASED only reschedules the restarts: q, cost, status, winning restart and the per-target success set
-    are identical to the single-launch result, on the host path (phased by default) and on the device path (on
-    request); evaluations are not compared (a single launch with parallel chunks runs speculative attempts)."""
+@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 6000, 24)])
+def test_dynamic_speed_batches_equal_static_schedule(name, T, R):
+    """Speed batches run as dynamic chains (restarts claimed on the device, idle lanes help unsolved targets in
+    parallel): q, cost, status, winning restart and the per-target success set are identical to the static
+    (target, chunk) schedule and to the lowest-index rule of the twin (lib.rs:409-412 with one thread), on the device
+    path and on the host path; evaluations are not compared (helpers run speculative attempts)."""
     import torch
     r, ch = robot_and_chain(name)
     tg, x0, lb, ub = _device_targets(r, ch, T, 11)
     cfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R)
-    q1, f1, s1, e1 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True)                  # device path, one launch
-    q2, f2, s2, e2 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True, phased=True)     # device path, phased
+    q1, f1, s1, e1 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True, static=True, chunks=1)  # every chain in order
+    q2, f2, s2, e2 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True)                          # dynamic chains
     ok = torch.as_tensor(cfg.is_success(s1.cpu().numpy()), device="cuda")
     assert torch.equal(s1, s2) and torch.equal(q1[ok], q2[ok]) and torch.equal(f1[ok], f2[ok])
     assert torch.equal(e1["restart"][ok], e2["restart"][ok])
-    q3, f3, s3, e3 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, stats=True)  # host path: phased
-    q4, f4, s4 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, phased=False)
+    assert torch.equal(q1[~ok], q2[~ok])  # unsolved targets: the first attempt's record, in both schedules
+    for variant in (1, 2):
+        q5, f5, s5 = r.ik_batch(cfg, tg, x0, restarts=R, variant=variant)
+        assert torch.equal(s5, s1) and torch.equal(q5[ok], q1[ok])
+    q3, f3, s3, e3 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, stats=True)  # host path
+    q4, f4, s4 = r.ik_batch(cfg, tg.cpu().numpy(), x0.cpu().numpy(), restarts=R, static=True)
     okh = ok.cpu().numpy()
     assert np.array_equal(s3, s1.cpu().numpy()) and np.array_equal(q3[okh], q1[ok].cpu().numpy())
     assert np.array_equal(e3["restart"][okh], e1["restart"][ok].cpu().numpy().astype(np.uint64))

@@ -210,7 +210,11 @@ def test_new_entry_points_check_their_arguments_before_touching_the_gpu():
 
 def test_batch_opts_flags_match_the_header():
     hdr = open(os.path.join(ROOT, "include", "optik_b200.h")).read()
-    for name, val in (("OPTIK_BATCH_ASYNC", ob.BATCH_ASYNC), ("OPTIK_BATCH_PHASED", ob.BATCH_PHASED),
-                      ("OPTIK_BATCH_SINGLE_LAUNCH", ob.BATCH_SINGLE_LAUNCH)):
+    for name, val in (("OPTIK_BATCH_ASYNC", ob.BATCH_ASYNC), ("OPTIK_BATCH_STATIC", ob.BATCH_STATIC)):
         assert f"#define {name} {val}u" in hdr
     assert f"#define OPTIK_RECORD_HEAD {ob.RECORD_HEAD}" in hdr
+    assert f"#define OPTIK_STATUS_CODE_MASK {ob.STATUS_CODE_MASK:#x}" in hdr
+    assert f"#define OPTIK_STATUS_FLAG_SEED_CLAMPED {ob.STATUS_FLAG_SEED_CLAMPED:#x}" in hdr
+    # a clamped-seed flag never changes the success classification (lib.rs:376-379 on the status code)
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=1)
+    assert list(cfg.is_success(np.array([1, 1 | 0x100, 5 | 0x100, 2]))) == [True, True, False, False]
