@@ -387,10 +387,12 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const size_t off_ev = ((direct && d_evals) || dyn) ? 0 : carve(njobs * sizeof(int));
   const bool use_found = speed && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
-  // dynamic chains: [queue | ctl[3] | next[T] | lock[T] | ticket ring] zeroed together, found[T] set to ~0
+  // dynamic chains: [queue | ticket head | ticket tail (one 128-byte line each) | next[T] | lock[T] | ticket ring] zeroed
+  // together, found[T] set to ~0
   unsigned help_cap = 1;
   if (dyn) while (help_cap < 4u * (unsigned)plan0.resident_tiles) help_cap <<= 1;
-  const size_t off_zero = carve(dyn ? 32 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned) : sizeof(unsigned long long));
+  const size_t dyn_zero = 384 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned);
+  const size_t off_zero = carve(dyn ? dyn_zero : sizeof(unsigned long long));
   const size_t off_dfound = dyn ? carve(T * sizeof(unsigned)) : 0;
   // selection: slice the candidate range when one target has very many chunks
   unsigned slices = 1;
@@ -424,8 +426,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   P.found = nullptr;
   if (dyn) {
     P.sched = 1;
-    P.dyn_ctl = (unsigned long long*)(sc + off_zero + 8);
-    P.dyn_next = (unsigned*)(sc + off_zero + 32);
+    P.dyn_ctl = (unsigned long long*)(sc + off_zero + 128);
+    P.dyn_next = (unsigned*)(sc + off_zero + 384);
     P.dyn_lock = P.dyn_next + T;
     P.help_slots = P.dyn_lock + T;
     P.help_mask = help_cap - 1;
@@ -433,10 +435,11 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     const uint64_t lanes = (uint64_t)plan0.resident_tiles;
     P.dyn_k0 = T >= lanes ? 0u : (unsigned)((lanes + T - 1) / T - 1);
     if (P.dyn_k0 > 7) P.dyn_k0 = 7;
-    CUDA_TRY(cudaMemsetAsync(sc + off_zero, 0, 32 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned), s));
+    CUDA_TRY(cudaMemsetAsync(sc + off_zero, 0, dyn_zero, s));
     CUDA_TRY(cudaMemsetAsync(P.dyn_found, 0xff, T * sizeof(unsigned), s));
     if (d_evals) CUDA_TRY(cudaMemsetAsync(d_evals, 0, T * sizeof(int32_t), s));
   } else {
+    P.sched = (per_attempt_records && tile == 1 && T == 1) ? 2 : 0;
     CUDA_TRY(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), s));
     if (use_found) {
       P.found = (unsigned long long*)(sc + off_found);

@@ -16,15 +16,18 @@
 // all lanes busy) -- a lone lane drawing a block inside this kernel stalls the 31 other lanes of its warp for ~800
 // instructions; the in-kernel draw remains as the fallback for restart indices beyond the table.
 // Scheduling (lib.rs:297-301, 381-387, 393-413): a flattened state machine, every lane runs ONE uniform loop body
-// (evaluate -> stop tests -> step) and takes its next attempt when one ends:
-//   sched 0  static jobs (target, chunk): chunk c runs restarts r_begin+c, +C, ... in order (Quality batches, per-attempt
-//            records, small Speed batches with the `found` early exit)
+// (evaluate -> stop tests -> step) and takes its next attempt when one ends.  The transition code is entered by the
+// whole warp (converged) whenever some lane needs work, so that queue fetches and ticket pops are warp-aggregated:
+//   sched 2  per-attempt records: job = one restart of the one target (optik_gpu_ik_attempts, BASELINE config 2)
+//   sched 0  static jobs (target, chunk): chunk c runs restarts r_begin+c, +C, ... in order (Quality batches, small
+//            Speed batches with the `found` early exit)
 //   sched 1  dynamic Speed chains: a lane that takes a target claims its restarts one by one (atomicAdd on next[t]) until
 //            one converges; once every target has been taken, lanes whose chain ended pop HELP TICKETS that failing
 //            chains push and claim restarts of the same target in parallel.  A claimed index always runs unless a LOWER
 //            index has already converged (found[t], lib.rs:308, 382-384), so the per-target answer is the lowest-index
 //            converged restart (lib.rs:409-412 with one thread) regardless of timing; no host round trip, no tail of
-//            unlucky targets.
+//            unlucky targets.  Tickets are hints (a lost one costs parallelism, never correctness); a warp leaves when
+//            every target has been taken, none of its lanes runs a chain and no ticket shows up for a few polls.
 #include <cuda_runtime.h>
 
 #include "ik_math.cuh"
@@ -92,21 +95,12 @@ __global__ void chacha8_kat_kernel(const uint32_t* __restrict__ key_g, unsigned 
   // words 8..15 of the block are not consumed by the solver (n <= 8 joints use 8 u64 = 16 words: all of them)
 }
 
-// ---- help-ticket queue of the dynamic scheduler (hints only: a lost ticket costs parallelism, never correctness)
+// ---- help-ticket ring of the dynamic scheduler: head = dyn_ctl[0], tail = dyn_ctl[16] (separate 128-byte lines).
+// Overflow overwrites unconsumed tickets and a consumer may read a slot twice (second time 0): both only lose hints.
+constexpr int CTL_TAIL = 16;
 DEV void help_push(const SolveParams& P, unsigned t) {
-  const unsigned long long head = *((volatile unsigned long long*)(P.dyn_ctl + 0));
-  const unsigned long long tail = *((volatile unsigned long long*)(P.dyn_ctl + 1));
-  if (tail - head >= (unsigned long long)(P.help_mask >> 1)) return;  // full enough
-  const unsigned long long s = atomicAdd(P.dyn_ctl + 1, 1ull);
+  const unsigned long long s = atomicAdd(P.dyn_ctl + CTL_TAIL, 1ull);
   atomicExch(P.help_slots + (unsigned)(s & P.help_mask), t + 1u);
-}
-DEV unsigned help_pop(const SolveParams& P) {  // -> target or DYN_NONE
-  const unsigned long long head = *((volatile unsigned long long*)(P.dyn_ctl + 0));
-  const unsigned long long tail = *((volatile unsigned long long*)(P.dyn_ctl + 1));
-  if (head >= tail) return DYN_NONE;
-  if (atomicCAS(P.dyn_ctl + 0, head, head + 1ull) != head) return DYN_NONE;  // lost the race; retry next iteration
-  const unsigned v = atomicExch(P.help_slots + (unsigned)(head & P.help_mask), 0u);
-  return v ? v - 1u : DYN_NONE;  // 0: the producer has not stored yet -- drop the hint
 }
 
 template <bool GENERAL, int ROWS>
@@ -143,98 +137,159 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   __syncthreads();
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
   double* qc = s_qc + tid;  // qc[j * T1_THREADS]
   double* qt_ = s_qt + tid;
   double2* const row0 = s_rows + (size_t)tid * units;  // rows[k] = row0 + k * row_stride
   const size_t row_stride = (size_t)T1_THREADS * units;
   double2 ltrial[ROWS == 1 ? 3 * 8 : 1];  // ROWS == 1: the trial point's body columns (thread-local memory)
-  const unsigned long long njobs = P.sched ? P.T : P.T * (unsigned long long)P.C;
+  const int sched = P.sched;
+  const unsigned long long njobs = sched == 1 ? P.T : P.T * (unsigned long long)P.C;
   const bool speed = (P.mode == 2);
-  const bool dyn = (P.sched != 0);
   const unsigned long long t_start = P.max_ns ? globaltimer_ns() : 0ull;
   const unsigned long long nrest = P.r_end - P.r_begin;
 
-  // ---- per-thread state.  Static: a "job" is one (target, chunk).  Dynamic: a "chain" on one target.
-  unsigned long long job = 0, tgt_id = 0, src_id = 0, r_idx = 0, r_next = 0;
-  bool running = false, job_open = false, best_has = false, rec_any = false, done = false, fresh_done = false;
+  // ---- per-thread state.  sched 0: a "job" is one (target, chunk); sched 1: a "chain" on one target; sched 2: one attempt
+  unsigned long long job = 0, tgt_id = 0, r_idx = 0, r_next = 0;
+  bool running = false, job_open = false, best_has = false, rec_any = false, done = false;
+  bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
+  int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
+  unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
 
   for (;;) {
-    // ---------------- transitions of idle threads: take the next attempt
-    if (!running && !done) {
+    // ---------------- transitions: lanes without an attempt take the next one.  Entered by the WHOLE warp (converged)
+    // whenever some lane needs work, so that queue fetches and ticket pops are one atomic per warp.
+    const unsigned need = __ballot_sync(FULLMASK, !running && !done);
+    if (need) {
+      const bool idle = !running && !done;
+      const bool late = P.max_ns && (globaltimer_ns() - t_start) > P.max_ns;  // lib.rs:260-264
       bool got = false;
-      if (!dyn) {
-        for (;;) {
-          if (!job_open) {
-            job = atomicAdd(P.queue, 1ull);  // dynamic job queue
-            if (job >= njobs) { done = true; break; }
-            const unsigned long long c = (P.C == 1) ? 0ull : (P.T == 1 ? job : job % P.C);
-            tgt_id = (P.C == 1) ? job : (P.T == 1 ? 0ull : job / P.C);
-            src_id = tgt_id;
-            r_next = P.r_begin + c;
-            best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
-            for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[src_id * n + j];  // record if no attempt runs
-            P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_next;
-            P.cand_status[job] = OPTIK_ST_SKIPPED;
-            job_open = true;
+      if (sched == 2) {
+        const int leader = __ffs(need) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(P.queue, (unsigned long long)__popc(need));
+        base = __shfl_sync(FULLMASK, base, leader);
+        if (idle) {
+          job = base + __popc(need & ((1u << lane) - 1u));
+          if (job >= njobs) done = true;
+          else {
+            r_idx = P.r_begin + job;
+            if (!late) got = true;
+            else {  // past the deadline: the attempt is recorded as not run
+#pragma unroll 1
+              for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[j];
+              P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_idx;
+              P.cand_status[job] = OPTIK_ST_SKIPPED; P.cand_evals[job] = 0;
+            }
           }
-          bool go = r_next < P.r_end;
-          if (go && speed && P.found) go = !(*((volatile unsigned long long*)(P.found + tgt_id)) < r_next);
-          if (go && P.max_ns) go = !((globaltimer_ns() - t_start) > P.max_ns);
-          if (go) { r_idx = r_next; r_next += P.C; got = true; break; }
-          P.cand_evals[job] = job_evals;  // the chunk is finished
-          job_open = false;
+        }
+      } else if (sched == 0) {
+        if (idle) {
+          for (;;) {
+            if (!job_open) {
+              job = atomicAdd(P.queue, 1ull);  // dynamic job queue
+              if (job >= njobs) { done = true; break; }
+              const unsigned long long c = (P.C == 1) ? 0ull : (P.T == 1 ? job : job % P.C);
+              tgt_id = (P.C == 1) ? job : (P.T == 1 ? 0ull : job / P.C);
+              r_next = P.r_begin + c;
+              best_has = false; rec_any = false; best_score = 0.0; job_evals = 0;
+              job_open = true;
+            }
+            bool go = r_next < P.r_end && !late;
+            if (go && speed && P.found) go = !(*((volatile unsigned long long*)(P.found + tgt_id)) < r_next);
+            if (go) { r_idx = r_next; r_next += P.C; got = true; break; }
+            if (!rec_any) {  // the chunk ran no attempt: its record says so
+#pragma unroll 1
+              for (int j = 0; j < n; j++) P.cand_q[job * n + j] = P.x0[tgt_id * n + j];
+              P.cand_f[job] = 0.0; P.cand_score[job] = 0.0; P.cand_restart[job] = r_next;
+              P.cand_status[job] = OPTIK_ST_SKIPPED;
+            }
+            P.cand_evals[job] = job_evals;  // the chunk is finished
+            job_open = false;
+          }
         }
       } else {
-        for (int tries = 0; tries < 4; tries++) {  // bounded: stale tickets are retried in the next pass
-          if (job_open) {  // continue my chain: claim the next restart unless a restart already converged
-            bool go = *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE;
-            if (go && P.max_ns) go = !((globaltimer_ns() - t_start) > P.max_ns);
-            if (go) {
-              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + tgt_id, 1u);
-              if (rel < nrest) { r_idx = P.r_begin + rel; got = true; break; }
-            }
-            job_open = false;  // chain over
-            atomicAdd(P.dyn_ctl + 2, ~0ull);
+        // (A) continue my chain: claim the next restart unless a restart of the target already converged
+        if (idle && job_open) {
+          if (!late && *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE) {
+            const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + tgt_id, 1u);
+            if (rel < nrest) { r_idx = P.r_begin + rel; got = true; }
           }
-          unsigned t = DYN_NONE;
-          if (!fresh_done) {
-            const unsigned long long f = atomicAdd(P.queue, 1ull);
-            if (f < P.T) {  // a fresh target: default record (kept if no attempt ever runs), then -- with fewer targets
-              t = (unsigned)f;  // than resident lanes -- tickets for parallel chains from the start
+          if (!got) job_open = false;  // chain over
+        }
+        // (B) fresh targets, one queue fetch per warp
+        unsigned want = __ballot_sync(FULLMASK, idle && !got);
+        if (want && !wfd) {
+          const int leader = __ffs(want) - 1;
+          unsigned long long base = 0;
+          if (lane == leader) base = atomicAdd(P.queue, (unsigned long long)__popc(want));
+          base = __shfl_sync(FULLMASK, base, leader);
+          if (idle && !got) {
+            const unsigned long long f = base + __popc(want & ((1u << lane) - 1u));
+            if (f < P.T) {  // default record (kept if no attempt ever runs), then -- with fewer targets than resident
+              tgt_id = f;   // lanes -- tickets for parallel chains from the start
+#pragma unroll 1
               for (int j = 0; j < n; j++) P.cand_q[f * n + j] = P.x0[f * n + j];
               P.cand_f[f] = 0.0; P.cand_status[f] = OPTIK_ST_SKIPPED;
               if (P.cand_restart) P.cand_restart[f] = P.r_begin;
               if (P.dyn_k0) {
                 __threadfence();
-                for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, t);
+                for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, (unsigned)f);
               }
-            } else fresh_done = true;
-          }
-          if (t == DYN_NONE && fresh_done) {
-            t = help_pop(P);
-            if (t == DYN_NONE) {
-              if (*((volatile unsigned long long*)(P.dyn_ctl + 2)) == 0ull) done = true;  // no chain anywhere: finished
-              break;  // otherwise poll again in the next pass
+              if (!late) {
+                const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + f, 1u);
+                if (rel < nrest) { r_idx = P.r_begin + rel; got = true; job_open = true; }
+              }
             }
-            if (*((volatile unsigned*)(P.dyn_found + t)) != DYN_NONE) continue;  // stale ticket
           }
-          if (t == DYN_NONE) continue;
-          tgt_id = src_id = job = t;
-          job_open = true;
-          atomicAdd(P.dyn_ctl + 2, 1ull);
+          if (base + __popc(want) >= P.T) wfd = true;
+          want = __ballot_sync(FULLMASK, idle && !got);
+        }
+        // (C) help tickets, one pop of k tickets per warp
+        if (want && wfd && !late) {
+          const int leader = __ffs(want) - 1;
+          unsigned long long h = 0;
+          unsigned k = 0;
+          if (lane == leader) {
+            h = *((volatile unsigned long long*)(P.dyn_ctl + 0));
+            const unsigned long long tl = *((volatile unsigned long long*)(P.dyn_ctl + CTL_TAIL));
+            if (tl > h) {
+              k = (unsigned)min((unsigned long long)__popc(want), tl - h);
+              if (atomicCAS(P.dyn_ctl + 0, h, h + k) != h) k = 0;  // lost the race; next pass
+            }
+          }
+          h = __shfl_sync(FULLMASK, h, leader);
+          k = __shfl_sync(FULLMASK, k, leader);
+          const unsigned rank = __popc(want & ((1u << lane) - 1u));
+          if (idle && !got && rank < k) {
+            const unsigned v = atomicExch(P.help_slots + (unsigned)((h + rank) & P.help_mask), 0u);
+            if (v && *((volatile unsigned*)(P.dyn_found + (v - 1u))) == DYN_NONE) {
+              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + (v - 1u), 1u);
+              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; }
+            }
+          }
+        }
+        // leave when nothing is left to do here: all targets taken, no chain in this warp, no ticket for a few polls
+        n_idle = __popc(__ballot_sync(FULLMASK, idle && !got));
+        if (wfd) {
+          if (__any_sync(FULLMASK, running || got)) idle_polls = 0;
+          else if (late || ++idle_polls > 6) { if (idle) done = true; }
+          else __nanosleep(1000);
         }
       }
       if (got) {  // restart 0 = the caller's seed, i >= 1 = ChaCha8 stream i (lib.rs:360-370)
         if (r_idx == 0) {
+#pragma unroll 1
           for (int j = 0; j < n; j++) {
             const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-            qt_[j * T1_THREADS] = fmin(fmax(P.x0[src_id * n + j], jc[12]), jc[13]);
+            qt_[j * T1_THREADS] = fmin(fmax(P.x0[tgt_id * n + j], jc[12]), jc[13]);
           }
         } else if (r_idx - P.seed_begin < P.seed_count) {
           const double* sd = P.seed_tab + (r_idx - P.seed_begin) * n;
+#pragma unroll 1
           for (int j = 0; j < n; j++) qt_[j * T1_THREADS] = __ldg(sd + j);
         } else {
           uint64_t u[8];
@@ -249,10 +304,9 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
         running = true;
       }
+      if (__all_sync(FULLMASK, done)) break;
     }
-    if (__all_sync(FULLMASK, done)) break;
-    if (!__any_sync(FULLMASK, running)) { __nanosleep(400); continue; }  // dynamic mode: every lane is polling for tickets
-    if (!running) continue;
+    if (!running) continue;  // meets the rest of the warp again at the ballot
 
     // ---------------- evaluate the trial point: backward recursion on the inverse pose, base frame
     double2* trow = (ROWS == 1) ? ltrial : row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
@@ -287,7 +341,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       Ci.q = qmul(Ci.q, lq);
       Ci.t = sub3(Ci.t, qrot(Ci.q, lt));
     }
-    const se3 tgt = load_pose8(P.targets + 8 * src_id);
+    const se3 tgt = load_pose8(P.targets + 8 * tgt_id);
     se3 B;  // X = (C_0 T_tgt)^-1
     {
       const qt xiq = qmul(Ci.q, tgt.q);
@@ -317,6 +371,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       if (df < P.tol_df_eff) status = OPTIK_ST_FTOL;
       else if (P.tol_dx > 0.0) {
         double dx = 0.0;
+#pragma unroll 1
         for (int j = 0; j < n; j++) dx = fmax(dx, fabs(qt_[j * T1_THREADS] - qc[j * T1_THREADS]));
         if (dx < P.tol_dx) status = OPTIK_ST_XTOL;
       }
@@ -329,8 +384,8 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     }
     if (status == OPTIK_ST_NONE && evals >= P.max_evals) status = OPTIK_ST_ITERCAP;
     if (status == OPTIK_ST_NONE && P.max_ns && (globaltimer_ns() - t_start) > P.max_ns) status = OPTIK_ST_SKIPPED;
-    if (status == OPTIK_ST_NONE && speed) {  // should_exit (lib.rs:308): a LOWER restart index of this target converged
-      if (dyn) {
+    if (status == OPTIK_ST_NONE && speed && (evals & 3) == 0) {  // should_exit (lib.rs:308): a LOWER restart index of
+      if (sched == 1) {                                            // this target converged (polled every 4th evaluation)
         if (*((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
       } else if (P.found && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
     }
@@ -341,23 +396,27 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
                            (P.tol_dx >= 0.0 && status == OPTIK_ST_XTOL);  // lib.rs:376-379
       n_attempts++; n_evals += evals;
       if (success) n_conv++;
-      if (!dyn) {
+      if (sched != 1) {
         double score = 0.0;
-        if (success && !speed)  // Quality score ||q - x0||^2 (lib.rs:402-407)
+        if (success && !speed) {  // Quality score ||q - x0||^2 (lib.rs:402-407)
+#pragma unroll 1
           for (int j = 0; j < n; j++) {
-            const double d = qt_[j * T1_THREADS] - P.x0[src_id * n + j];
+            const double d = qt_[j * T1_THREADS] - P.x0[tgt_id * n + j];
             score = fma(d, d, score);
           }
+        }
         job_evals += evals;
-        const bool record = success ? (!best_has || score < best_score) : !rec_any;  // failures: keep the first
+        const bool record = sched == 2 || (success ? (!best_has || score < best_score) : !rec_any);  // failures: keep the first
         if (record) {
           rec_any = true;
+#pragma unroll 1
           for (int j = 0; j < n; j++) P.cand_q[job * n + j] = qt_[j * T1_THREADS];
           P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
+          if (sched == 2) P.cand_evals[job] = evals;
         }
         if (success) {
           if (record) { best_has = true; best_score = score; }
-          if (speed) {  // first success ends the chunk (lib.rs:381-387, 411)
+          if (speed && sched == 0) {  // first success ends the chunk (lib.rs:381-387, 411)
             if (P.found) atomicMin(P.found + tgt_id, r_idx);
             r_next = P.r_end;
           }
@@ -376,6 +435,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
             if (atomicCAS(P.dyn_lock + tgt_id, 0u, 1u) == 0u) {
               const unsigned fnow = *((volatile unsigned*)(P.dyn_found + tgt_id));
               if (success ? fnow == rel : fnow == DYN_NONE) {
+#pragma unroll 1
                 for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
                 P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
                 if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
@@ -386,15 +446,11 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
             }
           }
         }
-        // a failing chain invites helpers once every target has been taken (they claim this target's next restarts in
-        // parallel); how many depends on how many lanes have nothing else to do
-        if (!success && status != OPTIK_ST_SKIPPED && *((volatile unsigned long long*)P.queue) >= P.T) {
-          const unsigned long long live = *((volatile unsigned long long*)(P.dyn_ctl + 2));
-          const unsigned long long lanes = (unsigned long long)gridDim.x * T1_THREADS;
-          unsigned h = 1;
-          if (live * 2 < lanes) h = 2;
-          if (live * 4 < lanes) h = 3;
-          for (unsigned k = 0; k < h; k++) help_push(P, (unsigned)tgt_id);
+        // a failing chain invites helpers once every target has been taken: they claim this target's next restarts in
+        // parallel (two when half of this warp's lanes were left without work by the last transition pass)
+        if (!success && status != OPTIK_ST_SKIPPED && wfd) {
+          help_push(P, (unsigned)tgt_id);
+          if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
         }
       }
       running = false;
@@ -402,6 +458,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     }
 
     if (accept) {  // current point <- trial point; body columns -> task columns
+#pragma unroll 1
       for (int j = 0; j < n; j++) qc[j * T1_THREADS] = qt_[j * T1_THREADS];
       fc = ft; have_cur = 1;
 #pragma unroll
