@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   // ---- per-thread state.  sched 0: a "job" is one (target, chunk); sched 1: a "chain" on one target; sched 2: one attempt
   unsigned long long job = 0, tgt_id = 0, r_idx = 0, r_next = 0;
   bool running = false, job_open = false, best_has = false, rec_any = false, done = false;
+  bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
+  unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
   int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
   unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
@@ -214,7 +216,9 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       } else {
         // (A) continue my chain: claim the next restart unless a restart of the target already converged
         if (idle && job_open) {
-          if (!late && *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE) {
+          if (excl) {  // nobody else knows this target: its restart counter lives in a register
+            if (!late && my_next < nrest) { r_idx = P.r_begin + my_next; my_next++; got = true; }
+          } else if (!late && *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE) {
             const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + tgt_id, 1u);
             if (rel < nrest) { r_idx = P.r_begin + rel; got = true; }
           }
@@ -229,19 +233,21 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           base = __shfl_sync(FULLMASK, base, leader);
           if (idle && !got) {
             const unsigned long long f = base + __popc(want & ((1u << lane) - 1u));
-            if (f < P.T) {  // default record (kept if no attempt ever runs), then -- with fewer targets than resident
-              tgt_id = f;   // lanes -- tickets for parallel chains from the start
-#pragma unroll 1
-              for (int j = 0; j < n; j++) P.cand_q[f * n + j] = P.x0[f * n + j];
-              P.cand_f[f] = 0.0; P.cand_status[f] = OPTIK_ST_SKIPPED;
-              if (P.cand_restart) P.cand_restart[f] = P.r_begin;
-              if (P.dyn_k0) {
-                __threadfence();
-                for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, (unsigned)f);
-              }
-              if (!late) {
-                const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + f, 1u);
-                if (rel < nrest) { r_idx = P.r_begin + rel; got = true; job_open = true; }
+            if (f < P.T) {
+              tgt_id = f;
+              if (late) {  // past the deadline: the target's record says that nothing ran
+                for (int j = 0; j < n; j++) P.cand_q[f * n + j] = P.x0[f * n + j];
+                P.cand_f[f] = 0.0; P.cand_status[f] = OPTIK_ST_SKIPPED;
+                if (P.cand_restart) P.cand_restart[f] = P.r_begin;
+              } else if (nrest > 0) {
+                r_idx = P.r_begin; got = true; job_open = true;
+                excl = P.dyn_k0 == 0;
+                my_next = 1;
+                if (!excl) {  // fewer targets than resident lanes: tickets for parallel chains from the start
+                  atomicExch(P.dyn_next + f, 1u);
+                  __threadfence();
+                  for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, (unsigned)f);
+                }
               }
             }
           }
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
             const unsigned v = atomicExch(P.help_slots + (unsigned)((h + rank) & P.help_mask), 0u);
             if (v && *((volatile unsigned*)(P.dyn_found + (v - 1u))) == DYN_NONE) {
               const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + (v - 1u), 1u);
-              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; }
+              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; }
             }
           }
         }
@@ -281,16 +287,23 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         }
       }
       if (got) {  // restart 0 = the caller's seed, i >= 1 = ChaCha8 stream i (lib.rs:360-370)
-        if (r_idx == 0) {
-#pragma unroll 1
-          for (int j = 0; j < n; j++) {
-            const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-            qt_[j * T1_THREADS] = fmin(fmax(P.x0[tgt_id * n + j], jc[12]), jc[13]);
-          }
+        if (r_idx == 0) {  // (loads issued together: one memory latency, not n)
+          double sv[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) if (j < n) sv[j] = P.x0[tgt_id * n + j];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < n) {
+              const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
+              qt_[j * T1_THREADS] = fmin(fmax(sv[j], jc[12]), jc[13]);
+            }
         } else if (r_idx - P.seed_begin < P.seed_count) {
           const double* sd = P.seed_tab + (r_idx - P.seed_begin) * n;
-#pragma unroll 1
-          for (int j = 0; j < n; j++) qt_[j * T1_THREADS] = __ldg(sd + j);
+          double sv[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) if (j < n) sv[j] = __ldg(sd + j);
+#pragma unroll
+          for (int j = 0; j < 8; j++) if (j < n) qt_[j * T1_THREADS] = sv[j];
         } else {
           uint64_t u[8];
           chacha8_block(P.key, r_idx, u);
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     if (status == OPTIK_ST_NONE && P.max_ns && (globaltimer_ns() - t_start) > P.max_ns) status = OPTIK_ST_SKIPPED;
     if (status == OPTIK_ST_NONE && speed && (evals & 3) == 0) {  // should_exit (lib.rs:308): a LOWER restart index of
       if (sched == 1) {                                            // this target converged (polled every 4th evaluation)
-        if (*((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
+        if (!excl && *((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
       } else if (P.found && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
     }
 
@@ -422,35 +435,54 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           }
         }
       } else {
-        // dynamic chains: the target's record is the lowest-index converged attempt, or the first attempt's failure.
-        // Writers serialise on a per-target lock and re-check found[t] under it, so the row is never torn.
+        // dynamic chains: the target's record is the lowest-index converged attempt, or the first attempt's failure
         const unsigned rel = (unsigned)(r_idx - P.r_begin);
-        bool write = false;
-        if (success) write = atomicMin(P.dyn_found + tgt_id, rel) > rel;
-        else write = (rel == 0u) && status != OPTIK_ST_SKIPPED;
-        if (P.cand_evals) atomicAdd(P.cand_evals + tgt_id, evals);
-        if (write) {
-          bool locked = false;
-          while (!locked) {
-            if (atomicCAS(P.dyn_lock + tgt_id, 0u, 1u) == 0u) {
-              const unsigned fnow = *((volatile unsigned*)(P.dyn_found + tgt_id));
-              if (success ? fnow == rel : fnow == DYN_NONE) {
+        if (P.cand_evals) atomicAdd(P.cand_evals + tgt_id, evals);  // (a reduction: no result, no wait)
+        if (excl) {  // the only chain on this target: plain stores
+          if (success || rel == 0u) {
 #pragma unroll 1
-                for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
-                P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
-                if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
+            for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
+            P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
+            if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
+          }
+          if (success) job_open = false;  // first success ends the chain (lib.rs:381-387, 411)
+          else if (wfd && status != OPTIK_ST_SKIPPED && my_next < nrest) {
+            // every target has been taken: a failing chain invites helpers, which claim this target's next restarts in
+            // parallel (two when half of this warp's lanes were left without work by the last transition pass).  From
+            // here on the target is shared: restart counter, found[] and the record lock live in memory.
+            atomicExch(P.dyn_next + tgt_id, my_next);
+            __threadfence();
+            help_push(P, (unsigned)tgt_id);
+            if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
+            excl = false;
+          }
+        } else {
+          // shared target: writers serialise on a per-target lock and re-check found[t] under it, so the row is never
+          // torn and ends as the lowest-index converged attempt
+          bool write = false;
+          if (success) write = atomicMin(P.dyn_found + tgt_id, rel) > rel;
+          else write = (rel == 0u) && status != OPTIK_ST_SKIPPED;
+          if (write) {
+            bool locked = false;
+            while (!locked) {
+              if (atomicCAS(P.dyn_lock + tgt_id, 0u, 1u) == 0u) {
+                const unsigned fnow = *((volatile unsigned*)(P.dyn_found + tgt_id));
+                if (success ? fnow == rel : fnow == DYN_NONE) {
+#pragma unroll 1
+                  for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
+                  P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
+                  if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
+                }
+                __threadfence();
+                atomicExch(P.dyn_lock + tgt_id, 0u);
+                locked = true;
               }
-              __threadfence();
-              atomicExch(P.dyn_lock + tgt_id, 0u);
-              locked = true;
             }
           }
-        }
-        // a failing chain invites helpers once every target has been taken: they claim this target's next restarts in
-        // parallel (two when half of this warp's lanes were left without work by the last transition pass)
-        if (!success && status != OPTIK_ST_SKIPPED && wfd) {
-          help_push(P, (unsigned)tgt_id);
-          if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
+          if (!success && status != OPTIK_ST_SKIPPED && wfd) {
+            help_push(P, (unsigned)tgt_id);
+            if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
+          }
         }
       }
       running = false;

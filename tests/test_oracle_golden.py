@@ -112,6 +112,21 @@ def test_chacha20_block_structure_rfc7539():
     assert O.lib().oracle_rng_u64(42, 1, 9) == (b[2] | (b[3] << 32))
 
 
+CHACHA8_TC1 = ("3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e"
+               "984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42")
+
+
+def test_chacha8_known_answer_zero_key():
+    """Published ChaCha8 test vector (all-zero 256-bit key, zero nonce/stream, block 0): the keystream is the block's 16
+    output words in little-endian order -- pins the round function, the round count, the constants, the feed-forward and
+    the word order rand_chacha serialises (next_u32 = word i, next_u64 = word 2i | word 2i+1 << 32)."""
+    import ctypes as C
+    key = (C.c_uint32 * 8)()
+    out = (C.c_uint32 * 16)()
+    O.lib().oracle_chacha8_block(key, 0, 0, out)
+    assert np.array(list(out), dtype="<u4").tobytes().hex() == CHACHA8_TC1
+
+
 def test_restart_seeds_uniform_in_limits(ur3e):
     qs = np.array([ur3e.restart_seed(i) for i in range(1, 2001)])
     assert np.all(qs >= ur3e.lb) and np.all(qs <= ur3e.ub)

@@ -95,3 +95,29 @@ def test_unreachable_target_fails():  # tests/test_ik.rs:24-43 (impossible goal)
     tgt = O.pose8([0, 0, 0, 1], [100.0, 100.0, 100.0])
     res = O.twin_ik(ch, tgt, np.zeros(6), 0, 16, "speed")
     assert not res["found"]
+
+
+def test_twin_vs_slsqp_standin_per_target():
+    """CPU-side version of tests/test_gpu_parity.py::test_solve_against_slsqp_standin on a small sample: the LM twin (==
+    the kernel, bit for bit) and the SLSQP stand-in agree on per-target success, and polished from the same start they
+    land on the same solution (<= 1e-6 rad)."""
+    import slsqp_standin as S
+    ch = chain("ur3e")
+    rng = np.random.default_rng(12)
+    P = O.twin_params(layout=1)
+    PP = O.twin_params(tol_f=1e-20, layout=1, max_evals=64)
+    agree = n = 0
+    worst = 0.0
+    for t in range(120):
+        tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
+        x0 = rng.uniform(ch.lb, ch.ub)
+        a = O.twin_ik(ch, tgt, x0, 0, 100, "speed", P)
+        found, q_s, _, _ = S.slsqp_ik(ch, tgt, x0, 100)
+        agree += a["found"] == found
+        if a["found"] and found:
+            qa, fa, sa, ea = O.twin_attempts(ch, tgt, a["q"], 0, 1, PP)
+            okp, qp = S.slsqp_polish(ch, tgt, a["q"], 1e-20)
+            if sa[0] == 1 and okp:
+                n += 1
+                worst = max(worst, np.abs(qa[0] - qp).max())
+    assert agree == 120 and n >= 60 and worst <= 1e-6, (agree, n, worst)

@@ -8,7 +8,7 @@ import optik_b200 as ob
 dev = torch.device("cuda", 0)
 
 
-def step_times(R=65536, variant=0, reps=10, flush=None):
+def step_times(R=65536, variant=0, reps=10, flush=None, max_evals=0):
     r = ob.Robot.named("panda")
     lb, ub = map(np.array, r.joint_limits())
     rng = np.random.default_rng(42)
@@ -25,12 +25,12 @@ def step_times(R=65536, variant=0, reps=10, flush=None):
         torch.cuda.synchronize()
         if i == 2: cnt.zero_()
         e0.record()
-        out = r.ik_attempts(cfg, targets[i], x0, R, best=True, counters=cnt, variant=variant)
+        out = r.ik_attempts(cfg, targets[i], x0, R, best=True, counters=cnt, variant=variant, max_evals=max_evals)
         e1.record(); torch.cuda.synchronize()
         if i >= 2: ts.append(e0.elapsed_time(e1))
     c = cnt.cpu().numpy()
     ms = float(np.median(ts))
-    print(f"step R={R} variant={variant}: median {ms:.4f} ms min {min(ts):.4f}  conv/s={c[2]/reps/ms*1e3:.3e} evals/s={c[1]/reps/ms*1e3:.3e} evals/att={c[1]/c[0]:.2f}", flush=True)
+    print(f"step R={R} variant={variant} max_evals={max_evals}: median {ms:.4f} ms min {min(ts):.4f}  conv/s={c[2]/reps/ms*1e3:.3e} evals/s={c[1]/reps/ms*1e3:.3e} evals/att={c[1]/c[0]:.2f}", flush=True)
 
 
 def batch(name, T, R, mode="speed", static=False, variant=0, chunks=0, reps=3):
@@ -61,6 +61,7 @@ if __name__ == "__main__":
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
         for v in (1, 2):
             step_times(65536, v, flush=flush)
+            step_times(65536, v, flush=flush, max_evals=24)
             step_times(1 << 20, v, reps=3)
     if what in ("all", "batch"):
         for v in (1, 2):
