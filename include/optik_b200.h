@@ -211,7 +211,10 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
  * solved exactly (closed form instead of the reference's interior-point solve; see csrc/diffik_kernel.cu).
  *   x0 [B][n]; V_WE [B][6] world-frame twist [linear; angular] (or one twist when shared_V != 0);
  *   v_max [B][n] (or one vector when shared_vmax != 0), every entry > 0
- *   alpha_out [B], v_out [B][n], status_out [B]: 1 = solved, 0 = no solution (rank-deficient Jacobian == None)
+ *   alpha_out [B], v_out [B][n], status_out [B]: 1 = solved.  The LP is always feasible and bounded (the reference
+ *   returns Some((alpha, v)), lib.rs:231-238): at a singular configuration a twist outside the Jacobian's range gives
+ *   alpha = 0, v = 0, one inside it the basic solution scaled into the velocity box; 0 is kept for "no solution"
+ *   (not produced by the current kernel)
  * num_positions must be 6 (the reference's case) or 7; otherwise OPTIK_ERR_UNSUPPORTED.  memory: 0 host, 1 device. */
 int optik_gpu_diff_ik_batch(const optik_robot* robot, const double* x0, const double* V_WE, int shared_V,
                             const double* v_max, int shared_vmax, uint64_t B, const double* ee_offset, int memory,

@@ -11,7 +11,10 @@
 // Steps per thread: inverse-pose backward recursion (as eval_kernel) -> body Jacobian columns -> rotate into the world
 // frame -> Gauss-Jordan with complete pivoting on the 6 x (n+1) augmented matrix [J_W | V] -> scale.
 // The matrix lives in shared memory, interleaved by thread ([entry][thread]) so that the data-dependent row/column
-// indices of the pivoting never cause bank conflicts.  Rank-deficient Jacobians report "no solution" (== None).
+// indices of the pivoting never cause bank conflicts.  The LP is always feasible (alpha = 0, v = 0) and bounded, so the
+// reference returns Some((alpha, v)) at singular configurations too (lib.rs:231-238): with a rank-deficient J_W the
+// elimination stops at the reduced rank; an unreachable twist direction gives alpha = 0, v = 0, a consistent system
+// its basic solution scaled into the velocity box.
 #include <cuda_runtime.h>
 
 #include "ik_math.cuh"
@@ -82,8 +85,10 @@ __global__ void __launch_bounds__(DIK_THREADS) diffik_kernel(const __grid_consta
     for (int r = 0; r < 6; r++) MAT(r, n) = V[r];
     // ---- Gauss-Jordan, complete pivoting (first maximum in row-major order wins)
     unsigned used = 0, pcs = 0;  // used columns (bit mask), pivot column of row k (3 bits each)
-    bool regular = true;
-    for (int k = 0; k < 6 && regular; k++) {
+    int rank = 6;
+    double vnorm = 0.0;
+    for (int r = 0; r < 6; r++) vnorm = fmax(vnorm, fabs(V[r]));
+    for (int k = 0; k < 6; k++) {
       int br = -1, bc = -1;
       double best = 0.0;
       for (int r = k; r < 6; r++)
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(DIK_THREADS) diffik_kernel(const __grid_consta
           const double a = fabs(MAT(r, c));
           if (!((used >> c) & 1u) && a > best) { best = a; br = r; bc = c; }
         }
-      if (br < 0 || best <= 1e-12 * scale) { regular = false; break; }
+      if (br < 0 || best <= 1e-12 * scale) { rank = k; break; }
       if (br != k)
         for (int j = 0; j <= n; j++) { const double t = MAT(k, j); MAT(k, j) = MAT(br, j); MAT(br, j) = t; }
       used |= 1u << bc;
@@ -104,25 +109,30 @@ __global__ void __launch_bounds__(DIK_THREADS) diffik_kernel(const __grid_consta
         for (int j = 0; j <= n; j++) MAT(r, j) = fma(-f, MAT(k, j), MAT(r, j));
       }
     }
-    if (!regular) {
-      P.status_out[i] = 0;
-      P.alpha_out[i] = 0.0;
-      for (int j = 0; j < n; j++) P.v_out[i * n + j] = 0.0;
-      continue;
+    if (rank < 6) {
+      double resid = 0.0;
+      for (int r = rank; r < 6; r++) resid = fmax(resid, fabs(MAT(r, n)));
+      if (resid > 1e-9 * vnorm) {  // V is not in the range of J_W: the optimum is alpha = 0
+        P.status_out[i] = 1;
+        P.alpha_out[i] = 0.0;
+        for (int j = 0; j < n; j++) P.v_out[i * n + j] = 0.0;
+        continue;
+      }
     }
     // ---- v(t) = a + t b ; rows 0/1 of the (now free) matrix storage hold a_i / vmax_i and b_i / vmax_i per joint
     int fcol = -1;
-    for (int c = 0; c < n; c++) if (!((used >> c) & 1u)) fcol = c;
+    if (rank == 6) for (int c = 0; c < n; c++) if (!((used >> c) & 1u)) fcol = c;
     double av[6], bv[6];
-    for (int k = 0; k < 6; k++) { av[k] = MAT(k, n); bv[k] = fcol >= 0 ? -MAT(k, fcol) : 0.0; }
+    for (int k = 0; k < 6; k++) { av[k] = k < rank ? MAT(k, n) : 0.0; bv[k] = (fcol >= 0) ? -MAT(k, fcol) : 0.0; }
 #define CS(j) M[(0 * DIK_COLS + (j)) * DIK_THREADS]
 #define SS(j) M[(1 * DIK_COLS + (j)) * DIK_THREADS]
 #define AA(j) M[(2 * DIK_COLS + (j)) * DIK_THREADS]
 #define BB(j) M[(3 * DIK_COLS + (j)) * DIK_THREADS]
+    for (int j = 0; j < n; j++) { AA(j) = 0.0; BB(j) = 0.0; }  // joints without a pivot stay at rest
 #pragma unroll
     for (int k = 0; k < 6; k++) {
       const int c = (pcs >> (3 * k)) & 7;
-      AA(c) = av[k]; BB(c) = bv[k];
+      if (k < rank) { AA(c) = av[k]; BB(c) = bv[k]; }
     }
     if (fcol >= 0) { AA(fcol) = 0.0; BB(fcol) = 1.0; }
     double gbest = 0.0, tbest = 0.0;

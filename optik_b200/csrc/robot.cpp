@@ -274,9 +274,12 @@ int choose_tile(int n, uint32_t want, bool batch) {
 }
 // thread-per-seed kernel: rows = 2 keeps the trial columns in shared memory (2 blocks/SM), rows = 1 in local memory
 // (3 blocks/SM).  opts.variant forces one; the default is the measured better one.
-int t1_rows(const optik_gpu_batch_opts* o) {
+int t1_rows(const optik_robot* r, const optik_gpu_batch_opts* o, double attempts) {
   if (o && (o->variant == 1 || o->variant == 2)) return (int)o->variant;
-  return OPTIK_T1_DEFAULT_ROWS;
+  // three blocks per SM win once every lane runs several attempts (throughput); with about one attempt per lane the
+  // launch is a latency chain and two blocks per SM with the trial columns in shared memory are faster
+  const double lanes1 = (double)r->sm_count * (r->occ_t1[0] > 0 ? r->occ_t1[0] : 3) * 128.0;
+  return attempts >= 4.0 * lanes1 ? 1 : 2;
 }
 Plan make_plan(const optik_robot* r, int tile, int rows, uint32_t blocks_req, unsigned long long njobs) {
   Plan p;
@@ -346,14 +349,14 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
                  unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
   const int tile = choose_tile(r->n, o ? o->tile : 0, true);
   if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (num_positions <= 8), 8, 16 or 32 and >= num_positions");
-  const int rows = t1_rows(o);
+  const bool speed = cfg->solution_mode == OPTIK_MODE_SPEED;
+  const int rows = t1_rows(r, o, per_attempt_records ? (double)R : (speed ? 2.0 * (double)T : (double)T * (double)(R < 4096 ? R : 4096)));
   SolveParams P{};
   fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
   P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
   P.max_ns = max_ns;
   P.counters = (unsigned long long*)d_counters;
   const int n = r->n;
-  const bool speed = cfg->solution_mode == OPTIK_MODE_SPEED;
   Plan plan0 = make_plan(r, tile, rows, o ? o->blocks : 0, ~0ull);
   // ---- scheduling.  Speed batches of the thread-per-seed kernel with enough targets run as dynamic chains (one launch,
   // restarts claimed on the device); everything else as static (target, chunk) jobs.
@@ -445,6 +448,11 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
       P.found = (unsigned long long*)(sc + off_found);
       CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
     }
+  }
+  {  // warp-level job pools: large enough to amortise the queue atomic, small enough to keep the tail balanced
+    const unsigned long long warps = (unsigned long long)plan.blocks * 4ull;
+    unsigned long long chunk = (dyn ? T : njobs) / (warps * 8ull);
+    P.pool_chunk = (unsigned)(chunk < 1 ? 1 : (chunk > 64 ? 64 : chunk));
   }
   if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, (P.has_prismatic || P.weighted) ? 1 : 0, rows, plan.blocks, s));
   else CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));

@@ -103,6 +103,41 @@ DEV void help_push(const SolveParams& P, unsigned t) {
   atomicExch(P.help_slots + (unsigned)(s & P.help_mask), t + 1u);
 }
 
+// ---- warp-level job pool.  `mask` = lanes that want a job (warp-uniform).  The pool [pool_next, pool_end) is a range
+// of the global queue claimed `chunk` jobs at a time by ONE atomic, so that most job starts cost no memory round trip;
+// on a refill `nb` is the new range's first job (the caller prefetches its inputs) else ~0.
+DEV unsigned long long warp_take(unsigned long long* queue, int lane, unsigned mask, unsigned chunk,
+                                 unsigned long long& pool_next, unsigned long long& pool_end, unsigned long long& nb) {
+  const unsigned k = __popc(mask), rank = __popc(mask & ((1u << lane) - 1u));
+  const unsigned long long avail = pool_end - pool_next;
+  nb = ~0ull;
+  if (avail >= k) {
+    const unsigned long long job = pool_next + rank;
+    pool_next += k;
+    return job;
+  }
+  const unsigned take = chunk > k ? chunk : k;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(queue, (unsigned long long)take);
+  base = __shfl_sync(FULLMASK, base, leader);
+  const unsigned long long job = rank < avail ? pool_next + rank : base + (rank - avail);
+  pool_next = base + (k - avail);
+  pool_end = base + take;
+  nb = base;
+  return job;
+}
+// L1 prefetch of the byte range [p, p + bytes) by the whole warp (at most 64 lines)
+DEV void warp_prefetch(const void* p, unsigned long long bytes, int lane) {
+  const char* b = (const char*)((unsigned long long)p & ~127ull);
+  const char* e = (const char*)p + bytes;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const char* a = b + 128ull * (unsigned)(lane + 32 * i);
+    if (a < e) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+  }
+}
+
 template <bool GENERAL, int ROWS>
 __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) double smem[];
@@ -157,6 +192,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
   int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
   unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
+  unsigned long long pool_next = 0, pool_end = 0;  // warp-uniform: this warp's claimed range of the job queue
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
@@ -170,12 +206,12 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       const bool late = P.max_ns && (globaltimer_ns() - t_start) > P.max_ns;  // lib.rs:260-264
       bool got = false;
       if (sched == 2) {
-        const int leader = __ffs(need) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(P.queue, (unsigned long long)__popc(need));
-        base = __shfl_sync(FULLMASK, base, leader);
+        unsigned long long nb;
+        const unsigned long long mine = warp_take(P.queue, lane, need, P.pool_chunk, pool_next, pool_end, nb);
+        if (nb < njobs && P.seed_tab && P.r_begin + nb >= P.seed_begin)  // the new range's seeds -> L1
+          warp_prefetch(P.seed_tab + (P.r_begin + nb - P.seed_begin) * n, (pool_end - nb) * n * sizeof(double), lane);
         if (idle) {
-          job = base + __popc(need & ((1u << lane) - 1u));
+          job = mine;
           if (job >= njobs) done = true;
           else {
             r_idx = P.r_begin + job;
@@ -227,12 +263,13 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         // (B) fresh targets, one queue fetch per warp
         unsigned want = __ballot_sync(FULLMASK, idle && !got);
         if (want && !wfd) {
-          const int leader = __ffs(want) - 1;
-          unsigned long long base = 0;
-          if (lane == leader) base = atomicAdd(P.queue, (unsigned long long)__popc(want));
-          base = __shfl_sync(FULLMASK, base, leader);
+          unsigned long long nb;
+          const unsigned long long f = warp_take(P.queue, lane, want, P.pool_chunk, pool_next, pool_end, nb);
+          if (nb < P.T) {  // the new range's seeds and targets -> L1
+            warp_prefetch(P.x0 + nb * n, (pool_end - nb) * n * sizeof(double), lane);
+            warp_prefetch(P.targets + nb * 8, (pool_end - nb) * 64, lane);
+          }
           if (idle && !got) {
-            const unsigned long long f = base + __popc(want & ((1u << lane) - 1u));
             if (f < P.T) {
               tgt_id = f;
               if (late) {  // past the deadline: the target's record says that nothing ran
@@ -251,7 +288,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
               }
             }
           }
-          if (base + __popc(want) >= P.T) wfd = true;
+          if (pool_next >= P.T) wfd = true;
           want = __ballot_sync(FULLMASK, idle && !got);
         }
         // (C) help tickets, one pop of k tickets per warp
@@ -324,6 +361,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     // ---------------- evaluate the trial point: backward recursion on the inverse pose, base frame
     double2* trow = (ROWS == 1) ? ltrial : row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
     se3 Ci = load_pose8(s_tip);  // C_n = tip^-1
+    const se3 tgt = load_pose8(P.targets + 8 * tgt_id);  // issued here: the recursion hides its latency
 #pragma unroll 1
     for (int j = n - 1; j >= 0; j--) {
       const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
@@ -354,7 +392,6 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       Ci.q = qmul(Ci.q, lq);
       Ci.t = sub3(Ci.t, qrot(Ci.q, lt));
     }
-    const se3 tgt = load_pose8(P.targets + 8 * tgt_id);
     se3 B;  // X = (C_0 T_tgt)^-1
     {
       const qt xiq = qmul(Ci.q, tgt.q);

@@ -25,7 +25,7 @@ enum {
 // The blob is n joints followed by the fixed tip pose8 {qx,qy,qz,qw,tx,ty,tz,0}.
 
 // Levenberg-Marquardt constants of the in-warp solver (tuned on Panda/UR5/UR3e/snake).
-#define OPTIK_LM_MAX_EVALS 32
+#define OPTIK_LM_MAX_EVALS 24
 #define OPTIK_LM_LAMBDA0 1e-1
 #define OPTIK_LM_LAMBDA_DEC 0.3
 #define OPTIK_LM_LAMBDA_INC 10.0
@@ -33,11 +33,6 @@ enum {
 #define OPTIK_LM_LAMBDA_MAX 1e6
 #define OPTIK_LM_STALL_REL 1e-1
 #define OPTIK_LM_STALL_COUNT 2
-
-// thread-per-seed kernel variant used by default: rows of column storage in shared memory (see solve_t1_kernel.cu)
-#ifndef OPTIK_T1_DEFAULT_ROWS
-#define OPTIK_T1_DEFAULT_ROWS 2
-#endif
 
 struct SolveParams {
   // problem
@@ -81,6 +76,7 @@ struct SolveParams {
   // thread-per-seed kernel, sched = 1: dynamic Speed chains (see solve_t1_kernel.cu).  The per-target record goes to
   // cand_q/f/status/restart[t] directly (cand_evals[t] += evaluations, zeroed by the host; cand_score unused).
   int sched;
+  unsigned pool_chunk;                // jobs a warp claims from the queue per atomic (sched 1, 2)
   unsigned dyn_k0;                    // help tickets pushed when a target is first taken (T < resident lanes)
   unsigned* dyn_next;                 // [T] next relative restart index to claim            (zeroed)
   unsigned* dyn_found;                // [T] lowest converged relative restart index so far  (0xffffffff)

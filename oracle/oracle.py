@@ -111,7 +111,7 @@ class Chain:
 
     # crates/optik/src/lib.rs:123-239 (the LP solved exactly, see diffik_oracle.c)
     def diff_ik(self, x0, V_WE, v_max, ee_offset=None):
-        """-> (alpha, v) or None (rank-deficient Jacobian)."""
+        """-> (alpha, v).  The LP is always feasible: at a singular configuration an unreachable twist gives alpha = 0."""
         alpha = C.c_double(0.0)
         v = np.zeros(self.n)
         rc = lib().oracle_diff_ik(_p(self.arr), self.njoints, _p(None if ee_offset is None else _d(ee_offset)), _p(_d(x0)),
@@ -163,7 +163,7 @@ class TwinParams(C.Structure):
 
 
 # defaults of the kernel's LM iteration (DESIGN.md "Solver"); keep in sync with optik_b200/csrc/solver_params.h
-LM_DEFAULTS = dict(max_evals=32, lambda0=1e-1, lambda_dec=0.3, lambda_inc=10.0, lambda_min=1e-9, lambda_max=1e6,
+LM_DEFAULTS = dict(max_evals=24, lambda0=1e-1, lambda_dec=0.3, lambda_inc=10.0, lambda_min=1e-9, lambda_max=1e6,
                    stall_rel=1e-1, stall_count=2, layout=0)
 
 

@@ -64,6 +64,14 @@ def main():
             alpha, v = solve_lp(world_jacobian(ch, x0), V, vmax)
             cases.append({"robot": name, "x0": list(x0), "V_WE": list(V), "v_max": list(vmax), "alpha": alpha,
                           "v": list(v) if ch.n == 6 else None})
+    # singular configurations (common home poses): the LP stays feasible and bounded, so the reference returns
+    # Some((alpha, v)) there too (lib.rs:231-238); a generic twist is unreachable => alpha = 0.  Only alpha is unique.
+    ur3e = O.Chain.from_urdf(open(os.path.join(ROOT, "optik_b200", "data", "ur3e.urdf")).read(), *LINKS["ur3e"])
+    for x0 in (np.zeros(6), np.array([0.0, -1.0, 0.0, 0.3, 0.0, 0.0]), np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])):
+        for V in (np.array([0.3, 0.1, 0.2, 0.5, 0.4, 0.6]), rng.random(6)):
+            alpha, v = solve_lp(world_jacobian(ur3e, x0), V, np.ones(6))
+            cases.append({"robot": "ur3e", "x0": list(x0), "V_WE": list(V), "v_max": [1.0] * 6, "alpha": alpha, "v": None,
+                          "singular": True})
     out = {"source": "scipy.optimize.linprog(method='highs') on the LP of kylc/optik@355e463 crates/optik/src/lib.rs:123-239; "
                      "J_W from oracle/optik_oracle.c (pinned to the reference's FK goldens)",
            "cases": cases}

@@ -58,8 +58,18 @@ def test_reference_property_bounds():  # tests/test_ik.rs:184-209
         assert np.all(v >= -1 - 1e-6) and np.all(v <= 1 + 1e-6)
 
 
-def test_singular_configuration_has_no_solution():
+def test_singular_configuration_gives_a_zero_step():
+    """The reference's LP is always feasible (alpha = 0, v = 0) and bounded: Clarabel reports Solved and diff_ik returns
+    Some((alpha, v)) at singular configurations too (lib.rs:231-238); an unreachable twist gives alpha = 0."""
     ch = chain("ur3e")
-    # wrist singularity (q5 = 0) makes the 6x6 Jacobian rank-deficient; a generic twist is then unreachable
+    V = [0.3, 0.1, 0.2, 0.5, 0.4, 0.6]
+    for x0 in (np.zeros(6), np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])):  # home pose; wrist singularity (q5 = 0)
+        alpha, v = ch.diff_ik(x0, V, np.ones(6))
+        assert alpha == 0.0 and np.all(v == 0.0)
+    # a twist inside the range of the singular Jacobian is followed: joint 1 alone at the wrist singularity
     x0 = np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])
-    assert ch.diff_ik(x0, [0.3, 0.1, 0.2, 0.5, 0.4, 0.6], np.ones(6)) is None
+    from tests_golden_helpers import world_jacobian
+    Jw = world_jacobian(ch, x0)
+    Vr = Jw[:, 0] * 0.5
+    alpha, v = ch.diff_ik(x0, Vr, np.ones(6))
+    assert alpha == 1.0 and np.abs(Jw @ v - Vr).max() < 1e-12

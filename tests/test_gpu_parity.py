@@ -574,6 +574,8 @@ def test_diff_ik_matches_lp_golden_and_oracle():
         assert res is not None
         alpha, v = res
         assert abs(alpha - c["alpha"]) <= 1e-8
+        if c.get("singular"):
+            continue  # alpha is the LP's unique optimum; v is not (any null-space vector inside the box)
         if c["v"] is not None:
             assert np.abs(np.array(v) - np.array(c["v"])).max() <= 1e-8
         oa, ov = ch.diff_ik(c["x0"], c["V_WE"], c["v_max"])
@@ -620,14 +622,24 @@ def test_diff_ik_batch_properties(name):
 
 def test_diff_ik_edge_cases():
     r, ch = robot_and_chain("ur3e")
-    # wrist singularity: no solution (None), through every entry point
-    x0 = np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])
+    # singular configurations (home pose, wrist singularity): the LP is feasible and bounded, the reference returns
+    # Some((alpha, v)) (lib.rs:231-238); an unreachable twist gives a zero step, through every entry point
     V = [0.3, 0.1, 0.2, 0.5, 0.4, 0.6]
-    assert r.diff_ik(x0, V, np.ones(6)) is None and ch.diff_ik(x0, V, np.ones(6)) is None
     import ctypes as C
     lib = ob.load_library()
     arr = lambda a: (C.c_double * len(a))(*a)
-    assert not lib.optik_robot_diff_ik(r._h, arr(x0), arr(V), arr([1.0] * 6))
+    for x0 in (np.zeros(6), np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])):
+        alpha, v = r.diff_ik(x0, V, np.ones(6))
+        assert alpha == 0.0 and np.all(np.array(v) == 0.0)
+        assert ch.diff_ik(x0, V, np.ones(6))[0] == 0.0
+        p0 = lib.optik_robot_diff_ik(r._h, arr(x0), arr(V), arr([1.0] * 6))
+        assert p0 and np.all(ob._take(p0, 6) == 0.0)
+    # a twist inside the range of the singular Jacobian is followed
+    from tests_golden_helpers import world_jacobian
+    x0 = np.array([0.3, -1.0, 1.2, 0.4, 0.0, 0.2])
+    Jw = world_jacobian(ch, x0)
+    alpha, v = r.diff_ik(x0, 0.5 * Jw[:, 0], np.ones(6))
+    assert alpha == 1.0 and np.abs(Jw @ np.array(v) - 0.5 * Jw[:, 0]).max() < 1e-9
     p = lib.optik_robot_diff_ik(r._h, arr([0.3, -1.0, 1.2, 0.4, 0.7, 0.2]), arr(V), arr([1.0] * 6))
     assert p
     v = ob._take(p, 6)
@@ -661,7 +673,7 @@ def test_cpp_consumer_end_to_end(name, tmp_path):
     assert m, p.stdout
     solved, accurate, dik, jac = map(int, m.groups())
     assert solved >= 198 and accurate == solved and jac == 6 * (6 if name == "ur3e" else 7)
-    assert dik >= solved - 2  # a solution may sit at a singular pose (diff_ik -> None)
+    assert dik == solved  # diff_ik always has a solution (alpha = 0 at worst)
 
 
 @pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 6000, 24)])
@@ -754,11 +766,11 @@ def test_solve_against_slsqp_standin(name, R):
           UR3e, whose per-attempt success is 0.18 for both solvers: with 32 restarts each of them independently misses
           ~0.5 % of the targets);
       (2) both answers satisfy the reference's predicate f < tol_f inside the limits under the golden-pinned oracle;
-      (3) polished to f < 1e-20 from the SAME start (the GPU's answer), both solvers land within 1e-6 rad of each other
-          (for the 7-DOF arm: in the pose-changing part of joint space; along the self-motion direction the solution
-          set is a continuum, reported);
-      (4) polished from their OWN answers, wherever both sit on the same IK branch (6-DOF arms: isolated solutions)
-          they agree to 1e-6 rad; the branch-match rate is reported."""
+      (3) polished to f < 1e-20 from the SAME start (the GPU's answer), both solvers land within 1e-6 rad of each other;
+      (4) polished from their OWN answers, wherever both sit on the same IK branch they agree to 1e-6 rad; the
+          branch-match rate is reported.
+    (3) and (4) need isolated solutions: for the 7-DOF arm, whose solutions form a one-parameter family (two polishers
+    drift ~1e-4 rad apart along the self-motion direction), they run with the redundancy locked (one joint held)."""
     import slsqp_standin as S
     r, ch = robot_and_chain(name)
     rng = np.random.default_rng(2024)
@@ -782,6 +794,26 @@ def test_solve_against_slsqp_standin(name, R):
     for t in both[:: max(1, len(both) // 400)]:  # (2)
         for sol in (q[t], q_ref[t]):
             assert ch.objective(sol, tg[t]) < cfg.tol_f and np.all(sol >= ch.lb) and np.all(sol <= ch.ub)
+    if ch.n > 6:
+        # joint-space comparisons need isolated solutions: lock the arm's redundancy (joint 3 held at 0.3 rad through
+        # lower == upper, in the kernel's clamp and in SLSQP's bounds alike) and solve targets reachable that way
+        arr = r.chain()
+        arr[2, 12] = arr[2, 13] = 0.3
+        r, ch = ob.Robot.from_chain(arr), O.Chain(arr)
+        T = 600
+        qs = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
+        tg = np.stack([ch.fk(qq)[1] for qq in qs])
+        x0 = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
+        q, f, st = r.ik_batch(cfg, tg, x0, restarts=R)
+        ok_l = cfg.is_success(st)
+        q_ref = np.zeros((T, ch.n))
+        ok_r = np.zeros(T, dtype=bool)
+        for t in range(T):
+            ok_r[t], qq, _, _ = S.slsqp_ik(ch, tg[t], x0[t], R)
+            if ok_r[t]:
+                q_ref[t] = qq
+        assert (ok_l == ok_r).mean() >= 0.99  # six joints, tight limits: a harder arm for both solvers
+        both = np.where(ok_l & ok_r)[0]
     # polish: the GPU path from given starts (one restart = the start itself), SLSQP with scipy
     TOLP = 1e-20
     pcfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=1, tol_f=TOLP)
@@ -795,8 +827,8 @@ def test_solve_against_slsqp_standin(name, R):
         okp, qp = S.slsqp_polish(ch, tg[t], q[t], TOLP)
         if okp:
             d = qa[i] - qp
-            same_start.append(np.abs(S.row_space_part(ch, qa[i], d) if ch.n > 6 else d).max())
-        if ch.n == 6 and np.abs(q[t] - q_ref[t]).max() < 0.05:  # same IK branch before polishing
+            same_start.append(np.abs(d).max())
+        if np.abs(q[t] - q_ref[t]).max() < 0.05:  # same IK branch before polishing
             branch += 1
             oko, qo = S.slsqp_polish(ch, tg[t], q_ref[t], TOLP)
             if oko:
@@ -805,8 +837,7 @@ def test_solve_against_slsqp_standin(name, R):
                 own_start.append(np.abs(qa[i] - qb[i]).max())
     assert len(same_start) >= 0.6 * len(sample)
     assert max(same_start) <= RAD_TOL, max(same_start)
-    if ch.n == 6:
-        assert len(own_start) > 50 and max(own_start) <= RAD_TOL, (len(own_start), max(own_start))
+    assert len(own_start) > 30 and max(own_start) <= RAD_TOL, (len(own_start), max(own_start))
     print(f"\n{name}: per-target success agreement {agree:.4f} (gpu {ok_gpu.mean():.4f}, slsqp {ok_ref.mean():.4f}); "
           f"same-start polish max |dq| {max(same_start):.2e} rad over {len(same_start)}; "
           f"same-branch rate {branch / max(len(sample), 1):.2f}, own-start polish max |dq| "
