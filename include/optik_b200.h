@@ -250,6 +250,10 @@ int optik_gpu_stream_create(const optik_robot* robot, void** stream_out);
 int optik_gpu_stream_sync(void* stream);
 void optik_gpu_stream_destroy(void* stream);
 
+/* Measurement helper (bench.py `roofline_solve`): fp64 FMA throughput of `device` in TFLOP/s, sustained over about
+ * `seconds` of launches of a register-only DFMA kernel (8 independent chains per thread); < 0 on error. */
+double optik_measure_fp64_peak(int device, double seconds);
+
 /* Pinned host allocations for fast, truly asynchronous host<->device copies. */
 void* optik_host_alloc(uint64_t bytes);
 void optik_host_free(void* p);

@@ -101,6 +101,7 @@ def load_library():
         "optik_gpu_stream_create": (C.c_int, [vp, C.POINTER(vp)]),
         "optik_gpu_stream_sync": (C.c_int, [vp]),
         "optik_gpu_stream_destroy": (None, [vp]),
+        "optik_measure_fp64_peak": (C.c_double, [C.c_int, C.c_double]),
         "optik_host_alloc": (vp, [C.c_uint64]),
         "optik_host_free": (None, [vp]),
     }

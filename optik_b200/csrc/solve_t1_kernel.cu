@@ -192,12 +192,15 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
   int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
   unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
+  unsigned n_help = 1;  // warp-uniform: tickets a failing chain pushes
   unsigned long long pool_next = 0, pool_end = 0;  // warp-uniform: this warp's claimed range of the job queue
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
 
+  unsigned pass = 0;  // warp-uniform loop counter
   for (;;) {
+    pass++;
     // ---------------- transitions: lanes without an attempt take the next one.  Entered by the WHOLE warp (converged)
     // whenever some lane needs work, so that queue fetches and ticket pops are one atomic per warp.
     const unsigned need = __ballot_sync(FULLMASK, !running && !done);
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         }
         // leave when nothing is left to do here: all targets taken, no chain in this warp, no ticket for a few polls
         n_idle = __popc(__ballot_sync(FULLMASK, idle && !got));
+        n_help = n_idle >= 16 ? 2u : 1u;
         if (wfd) {
           if (__any_sync(FULLMASK, running || got)) idle_polls = 0;
           else if (late || ++idle_polls > 6) { if (idle) done = true; }
@@ -434,10 +438,15 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     }
     if (status == OPTIK_ST_NONE && evals >= P.max_evals) status = OPTIK_ST_ITERCAP;
     if (status == OPTIK_ST_NONE && P.max_ns && (globaltimer_ns() - t_start) > P.max_ns) status = OPTIK_ST_SKIPPED;
-    if (status == OPTIK_ST_NONE && speed && (evals & 3) == 0) {  // should_exit (lib.rs:308): a LOWER restart index of
-      if (sched == 1) {                                            // this target converged (polled every 4th evaluation)
-        if (!excl && *((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
-      } else if (P.found && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
+    // should_exit (lib.rs:308): a LOWER restart index of this target converged.  Polled every 4th pass of the WARP (a
+    // warp-uniform condition: a per-lane one splits the warp in two for the rest of the loop body).
+    if (speed && (pass & 3u) == 0u) {
+      if (sched == 1) {
+        if (status == OPTIK_ST_NONE && !excl &&
+            *((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
+      } else if (P.found) {
+        if (status == OPTIK_ST_NONE && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
+      }
     }
 
     if (status != OPTIK_ST_NONE) {  // attempt over
@@ -485,12 +494,12 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           if (success) job_open = false;  // first success ends the chain (lib.rs:381-387, 411)
           else if (wfd && status != OPTIK_ST_SKIPPED && my_next < nrest) {
             // every target has been taken: a failing chain invites helpers, which claim this target's next restarts in
-            // parallel (two when half of this warp's lanes were left without work by the last transition pass).  From
-            // here on the target is shared: restart counter, found[] and the record lock live in memory.
+            // parallel (two when half of this warp's lanes were left without work by the last transition pass; pushing
+            // as many tickets as there are idle lanes was measured slower: stale tickets flood the ring).  From here on
+            // the target is shared: restart counter, found[] and the record lock live in memory.
             atomicExch(P.dyn_next + tgt_id, my_next);
             __threadfence();
-            help_push(P, (unsigned)tgt_id);
-            if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
+            for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
             excl = false;
           }
         } else {
@@ -516,10 +525,8 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
               }
             }
           }
-          if (!success && status != OPTIK_ST_SKIPPED && wfd) {
-            help_push(P, (unsigned)tgt_id);
-            if (n_idle >= 16) help_push(P, (unsigned)tgt_id);
-          }
+          if (!success && status != OPTIK_ST_SKIPPED && wfd)
+            for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
         }
       }
       running = false;
@@ -535,9 +542,11 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       double Jm[9], CJ[9];
       task_mats(ec, Jm, CJ);
       double2* wrow = (ROWS == 1) ? row0 : trow;  // ROWS == 2: converted in place, then the rows swap
+      double2 n0 = trow[0], n1 = trow[1], n2 = trow[2];  // software-pipelined: column j + 1 is in flight during column j
 #pragma unroll 1
       for (int j = 0; j < n; j++) {
-        const double2 a0 = trow[3 * j + 0], a1 = trow[3 * j + 1], a2 = trow[3 * j + 2];
+        const double2 a0 = n0, a1 = n1, a2 = n2;
+        if (j + 1 < n) { n0 = trow[3 * j + 3]; n1 = trow[3 * j + 4]; n2 = trow[3 * j + 5]; }
         v3 top, bot;
         task_col_m(Jm, CJ, mk3(a0.x, a0.y, a1.x), mk3(a1.y, a2.x, a2.y), top, bot);
         if (weighted) { top = weight3(tgt.q, P.wl, top); bot = weight3(tgt.q, P.wa, bot); }

@@ -72,3 +72,8 @@ if __name__ == "__main__":
         for T in (1 << 14, 1 << 16, 1 << 18, 1 << 20):
             batch("panda", T, 32, static=True)
         batch("ur5", 1 << 20, 32, static=True)
+    if what == "tail":
+        for T in (1 << 14, 1 << 16):
+            for R in (2, 4, 8, 16, 32):
+                batch("panda", T, R, variant=2)
+        batch("panda", 1 << 16, 32, variant=2, static=True, chunks=1)

@@ -1,5 +1,7 @@
-"""Launch sequence for ncu captures of the thread-per-seed kernel: the bench step (65 536 seeds, one Panda target) in both
-variants, and a Speed batch (262 144 Panda targets, dynamic chains)."""
+"""Launch sequence for ncu captures of the thread-per-seed kernel:
+  step     the bench step (65 536 seeds, one Panda target), both variants
+  speed    a Speed batch (1 Mi Panda targets, 32 restarts, dynamic chains)
+  quality  a Quality batch (262 144 Panda targets x 32 restarts, static jobs)"""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -9,23 +11,23 @@ r = ob.Robot.named("panda")
 lb, ub = map(np.array, r.joint_limits())
 rng = np.random.default_rng(42)
 dev = torch.device("cuda", 0)
-qstar = torch.from_numpy(rng.uniform(lb, ub, size=(4, 7))).to(dev)
-targets = r.eval_batch(qstar, want=("ee",))["ee"].contiguous()
-x0 = torch.from_numpy(0.5 * (lb + ub)).to(dev)
-cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=65536)
 which = sys.argv[1] if len(sys.argv) > 1 else "step"
 if which == "step":
+    qstar = torch.from_numpy(rng.uniform(lb, ub, size=(4, 7))).to(dev)
+    targets = r.eval_batch(qstar, want=("ee",))["ee"].contiguous()
+    x0 = torch.from_numpy(0.5 * (lb + ub)).to(dev)
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=65536)
     for v in (1, 2, 1, 2):
         r.ik_attempts(cfg, targets[0], x0, 65536, best=True, variant=v)
 else:
-    T = 1 << 18
+    T = (1 << 20) if which == "speed" else (1 << 18)
     lb_t, ub_t = torch.from_numpy(lb).to(dev), torch.from_numpy(ub).to(dev)
     g = torch.Generator(device="cuda").manual_seed(42)
     qs = torch.rand((T, 7), dtype=torch.float64, device=dev, generator=g) * (ub_t - lb_t) + lb_t
     x0s = (torch.rand((T, 7), dtype=torch.float64, device=dev, generator=g) * (ub_t - lb_t) + lb_t).contiguous()
     tg = r.eval_batch(qs, want=("ee",))["ee"].contiguous()
-    scfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=32)
-    for v in (1, 2, 1, 2):
-        r.ik_batch(scfg, tg, x0s, restarts=32, variant=v)
+    scfg = ob.SolverConfig(solution_mode=which, max_time=0.0, max_restarts=32)
+    for _ in range(3):
+        r.ik_batch(scfg, tg, x0s, restarts=32)
 torch.cuda.synchronize()
 print("done")
