@@ -163,7 +163,8 @@ typedef struct optik_gpu_batch_opts {
  * kernels and the D2H copies on `stream` and return WITHOUT waiting; outputs are valid after
  * optik_gpu_stream_sync(stream).  Inputs and outputs must stay alive until then and should be pinned
  * (optik_host_alloc), otherwise the copies are staged synchronously.  Two streams with two sets of buffers overlap
- * one call's transfers with the next call's kernels.  opts->counters is then SET (not incremented). */
+ * one call's transfers with the next call's kernels.  opts->counters is then SET (not incremented).  Seeds are
+ * validated on the device like device-memory calls (clamped + OPTIK_STATUS_FLAG_SEED_CLAMPED), not on the host. */
 #define OPTIK_BATCH_ASYNC 1u
 /* Speed-mode batches of the thread-per-seed kernel normally run as DYNAMIC CHAINS in one launch: a lane that takes a
  * target claims its restarts one by one on the device; once every target has been taken, idle lanes claim further

@@ -796,7 +796,11 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
       CUDA_TRY(optik_launch_flag_clamped((const double*)robot->chain_dev.p, n, x0, T, status_out, 1, s));
     return OPTIK_OK;
   }
-  if (int rc = check_seeds_host(robot, x0, T)) return rc;
+  // blocking host calls reject a seed outside the limits like the reference (lib.rs:251-254); enqueue-only calls leave
+  // the check to the device (clamp + OPTIK_STATUS_FLAG_SEED_CLAMPED): walking 1 Mi seeds on one host core costs more
+  // than their H2D copy
+  if (!async)
+    if (int rc = check_seeds_host(robot, x0, T)) return rc;
   // host-memory calls without a stream of their own serialise on the robot's stream
   std::unique_lock<std::mutex> lk(robot->mu, std::defer_lock);
   cudaStream_t s = (cudaStream_t)stream;
@@ -821,6 +825,8 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
                             evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
                             per_attempt, s, want_best ? (double*)(d + o_br) : nullptr))
     return rc;
+  if (async && r_begin == 0)
+    CUDA_TRY(optik_launch_flag_clamped((const double*)robot->chain_dev.p, n, (const double*)(d + o_x), T, (int*)(d + o_s), 1, s));
   CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(status_out, d + o_s, NO * 4, cudaMemcpyDeviceToHost, s));

@@ -250,3 +250,21 @@ def ref_ik_threaded(chain, target, x0, r_begin, r_end, mode="quality", threads=1
                C.byref(f), C.byref(rs), stats)
     assert found >= 0
     return dict(found=bool(found), q=q, f=f.value, restart=rs.value, attempts=stats[0], evals=stats[1], converged=stats[2])
+
+
+def ref_batch_threaded(chain, targets, x0, restarts, mode="speed", threads=1, params=None):
+    """A batch of independent targets, one target per worker thread (Robot::ik with set_parallelism(1) semantics per
+    target).  Returns (q (T, n), f (T,), found (T,) bool)."""
+    params = params or twin_params(layout=1 if chain.n <= 8 else 0)
+    targets, x0 = _d(targets), _d(x0)
+    T = targets.shape[0]
+    q = np.zeros((T, chain.n))
+    f = np.zeros(T)
+    found = np.zeros(T, dtype=np.int32)
+    fn = lib().ref_batch_threaded
+    fn.argtypes = [dp, C.c_int, C.POINTER(TwinParams), dp, dp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, dp, dp,
+                   C.POINTER(C.c_int)]
+    rc = fn(_p(chain.arr), chain.njoints, C.byref(params), _p(targets), _p(x0), chain.n, T, int(restarts),
+            2 if mode == "speed" else 1, int(threads), _p(q), _p(f), found.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return q, f, found.astype(bool)

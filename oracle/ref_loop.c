@@ -112,3 +112,48 @@ int ref_ik_threaded(const double* chain, int njoints, const double* ee_offset, c
   free(ws); free(th); free(c);
   return have;
 }
+
+/* ---- a batch of independent targets on the CPU: what a caller of the reference does with many IK problems
+ * (examples/example.rs:23-36 loops over targets) when it wants throughput -- one target per worker thread, each
+ * running Robot::ik with set_parallelism(1) semantics (restarts in index order, Speed stops at the first success,
+ * lib.rs:397-413).  Workers pull target indices from a shared counter.  No speculative work is wasted, so this is
+ * the most favourable CPU arrangement for a Speed-mode batch. */
+int twin_ik_c(const double* chain, int njoints, const double* ee_offset, const twin_params* P, const double* target,
+              const double* x0, uint64_t r_begin, uint64_t r_end, int mode, double* q_out, double* f_out,
+              int* status_out, uint64_t* restart_out);
+
+typedef struct {
+  const double* chain; int njoints; const twin_params* P;
+  const double* targets; const double* x0; int n; uint64_t T, R; int mode;
+  double* q_out; double* f_out; int* found_out;
+  atomic_ullong next;
+} batch_t;
+
+static void* batch_worker(void* arg) {
+  batch_t* B = (batch_t*)arg;
+  for (;;) {
+    uint64_t t = atomic_fetch_add(&B->next, 1);
+    if (t >= B->T) break;
+    int st; uint64_t rs; double f;
+    int have = twin_ik_c(B->chain, B->njoints, NULL, B->P, B->targets + 8 * t, B->x0 + (size_t)B->n * t, 0, B->R, B->mode,
+                         B->q_out + (size_t)B->n * t, &f, &st, &rs);
+    B->f_out[t] = f;
+    B->found_out[t] = have > 0;
+  }
+  return NULL;
+}
+
+int ref_batch_threaded(const double* chain, int njoints, const twin_params* P, const double* targets, const double* x0, int n,
+                       uint64_t T, uint64_t R, int mode, int threads, double* q_out, double* f_out, int* found_out) {
+  batch_t B;
+  memset(&B, 0, sizeof(B));
+  B.chain = chain; B.njoints = njoints; B.P = P; B.targets = targets; B.x0 = x0; B.n = n; B.T = T; B.R = R; B.mode = mode;
+  B.q_out = q_out; B.f_out = f_out; B.found_out = found_out;
+  atomic_init(&B.next, 0);
+  if (threads < 1) threads = 1;
+  pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+  for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, batch_worker, &B);
+  for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+  free(th);
+  return 0;
+}
