@@ -53,7 +53,7 @@ def workload_config(n_gpus):
         "robot": ROBOT, "dof": 7, "seeds_per_gpu_per_pass": SEEDS_PER_GPU, "targets_per_pass": 1,
         "solve_definition": "one restart attempt that converged (f<tol_f inside the joint limits, re-verified); the "
                             "per-target metric (IK problems solved per second) is the per_target block",
-        "parallelism": f"restart-range sharding over {n_gpus} GPU(s); one all-gather of 15 doubles/rank/pass "
+        "parallelism": f"restart-range sharding over {n_gpus} GPU(s); one exchange of 15 doubles/rank/pass "
                        "for the Quality best-pick" if n_gpus > 1 else "single GPU",
     }
 
@@ -436,9 +436,18 @@ def run_product(args):
     best = torch.empty((obd.RECORD_HEAD + n,), dtype=torch.float64, device=dev)
     tally = torch.zeros(3, dtype=torch.int64, device=dev)  # verified, claimed, passes with a global best
 
+    # cross-GPU best-pick: direct peer-to-peer stores over NVLink (two tiny kernels of ours); NCCL all-gather as fallback
+    px = None
+    if world > 1 and not args.nccl_exchange:
+        px = obd.PeerExchange.create(robot, rank, world, device=dev)
+        ok_all = torch.tensor([1.0 if px is not None else 0.0], device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if ok_all.item() < 1.0:
+            px = None
+
     def one_pass(tgt):
-        return obd.ik_restart_sharded(robot, cfg, tgt, x0, R, rank=rank, world=world, tile=tile,
-                                      counters=counters, out=rec, record=record, gathered=gathered, best=best)
+        return obd.ik_restart_sharded(robot, cfg, tgt, x0, R, rank=rank, world=world, tile=tile, counters=counters, out=rec,
+                                      record=record, gathered=gathered, best=best, exchange=px)
 
     def gate(tgt, best_rec):
         """success gate, OUTSIDE the timed region (between a pass's end event and the next start event), fully
@@ -562,7 +571,7 @@ def run_product(args):
         # depth 4: the NCCL kernel of pass s only gets SM resources once pass s+1's solve kernel drains, so a pass
         # completes about one pass late; four slots keep two solve kernels in flight regardless
         D = E2E_DEPTH_MULTI
-        pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=D, device=dev)
+        pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=D, device=dev, exchange=px)
         for s in range(D):  # warm the slots (NCCL stream setup)
             pipe.submit(s, tg_host[0], x0_host)
         for s in range(D):
@@ -687,8 +696,10 @@ def run_product(args):
                             "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
                             "the records and the global best, all on the pass's stream; %d passes in flight" % E2E_DEPTH_MULTI),
                     "blocking_call_value": sync_conv / sync_s, "blocking_call_ms_median": float(np.median(sync_times) * 1e3)},
-            # per pass: seed_table + solve_t1 + select (slice pass + final pass) [+ select_records]
-            "gpu_launches": (4 if world == 1 else 5) * NP,
+            # per pass: seed_table + solve_t1 + select (slice pass + final pass) [+ exchange push + select | select_records]
+            "gpu_launches": (4 if world == 1 else (6 if px is not None else 5)) * NP,
+            "exchange": (None if world == 1 else "peer-to-peer stores over NVLink (optik_gpu_exchange_push/_select)" if px is not None
+                         else "ncclAllGather + optik_gpu_select_records"),
             "roofline": roof,
             "roofline_solve": {"kernel": "solve_t1_kernel" if (tile or 1) == 1 else f"solve_kernel<{tile}>",
                                "bound": "fp64 issue / dependency latency (not HBM, not tensor)",
@@ -740,6 +751,7 @@ def main():
     ap.add_argument("--tile", type=int, default=0, help="lanes per restart seed: 8 (packed), 32 (one warp per seed); 0 = auto")
     ap.add_argument("--passes", type=int, default=0, help="passes per step; 0 = as many as make the timed region >= 1 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="use the NCCL all-gather for the cross-GPU best-pick")
     ap.add_argument("--headline-only", action="store_true", help="skip the per_target / configs blocks")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -245,6 +245,20 @@ int optik_gpu_chacha8_block(const optik_robot* robot, const uint32_t* key8, uint
 int optik_gpu_select_records(const optik_robot* robot, const double* records, uint32_t count, double* best_record_out,
                              void* stream);
 
+/* The same best-pick as DIRECT peer-to-peer stores over NVLink (no collective library call; csrc/exchange_kernel.cu).
+ * Every rank owns one zero-initialised SYMMETRIC buffer of optik_gpu_exchange_bytes(robot, world) bytes that the host
+ * has mapped into every peer (cudaIpc / torch symmetric memory); `peer_buffers_dev` is a device array of the `world`
+ * base addresses (this rank's own included).  Call number seq = 1, 2, ... (the same on every rank):
+ *   push    stores `record` into row `rank` of every peer's buffer and raises that row's flag to seq
+ *   select  waits (bounded, 2 s) for all `world` rows of call seq in the local buffer and applies the selection rule;
+ *           best_record_out[0] = -1 if a peer never delivered
+ * Both are asynchronous on `stream`; at most 4 calls may be in flight per rank (8 slots). */
+uint64_t optik_gpu_exchange_bytes(const optik_robot* robot, uint32_t world);
+int optik_gpu_exchange_push(const optik_robot* robot, const double* record, const uint64_t* peer_buffers_dev, uint32_t rank,
+                            uint32_t world, uint64_t seq, void* stream);
+int optik_gpu_exchange_select(const optik_robot* robot, const double* local_buffer, uint32_t world, uint64_t seq,
+                              double* best_record_out, void* stream);
+
 /* Streams for hosts without CUDA bindings of their own (Rust, ctypes): create on the robot's device, wait, destroy.
  * Any cudaStream_t the caller already owns may be passed to the batched calls instead. */
 int optik_gpu_stream_create(const optik_robot* robot, void** stream_out);

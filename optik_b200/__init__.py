@@ -94,6 +94,9 @@ def load_library():
         "optik_gpu_ik_attempts": (C.c_int, [vp, C.POINTER(_CSolverConfig), C.POINTER(_BatchOpts), vp, vp, vp, vp, vp, vp, vp]),
         "optik_gpu_eval_batch": (C.c_int, [vp, vp, vp, C.c_int, C.c_uint64, dp, dp, dp, C.c_int, vp, vp, vp, vp, vp]),
         "optik_gpu_select_records": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "optik_gpu_exchange_bytes": (C.c_uint64, [vp, C.c_uint32]),
+        "optik_gpu_exchange_push": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint64, vp]),
+        "optik_gpu_exchange_select": (C.c_int, [vp, vp, C.c_uint32, C.c_uint64, vp, vp]),
         "optik_gpu_restart_seeds": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, vp, vp]),
         "optik_gpu_chacha8_block": (C.c_int, [vp, vp, C.c_uint64, vp]),
         "optik_gpu_diff_ik_batch": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_uint64, vp, C.c_int, vp, vp, vp, vp]),

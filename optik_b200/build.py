@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "liboptik_b200.so")
-SRCS = ["solve_kernel.cu", "solve_t1_kernel.cu", "eval_kernel.cu", "diffik_kernel.cu", "peak_kernel.cu", "robot.cpp"]
+SRCS = ["solve_kernel.cu", "solve_t1_kernel.cu", "eval_kernel.cu", "diffik_kernel.cu", "peak_kernel.cu", "exchange_kernel.cu", "robot.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

@@ -37,6 +37,10 @@ extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm);
 extern "C" int optik_launch_seed_table(const double* chain, int n, const uint32_t* key_dev, unsigned long long r_begin,
                                        unsigned long long count, double* out, void* stream);
 extern "C" int optik_launch_chacha8_kat(const uint32_t* key_dev, unsigned long long stream_id, uint32_t* out16_dev, void* stream);
+extern "C" int optik_exchange_nslot(void);
+extern "C" int optik_launch_exchange_push(const double* rec, int len, const uint64_t* peers_dev, int rank, int W,
+                                          unsigned long long seq, void* stream);
+extern "C" int optik_launch_exchange_select(const double* buf, int W, int n, unsigned long long seq, double* out, void* stream);
 extern "C" int optik_launch_flag_clamped(const double* chain, int n, const double* x0, unsigned long long T, int* status,
                                          unsigned long long status_stride, void* stream);
 extern "C" int optik_launch_select_records(const double* rec, unsigned count, int n, double* out, void* stream);
@@ -639,6 +643,28 @@ int optik_gpu_chacha8_block(const optik_robot* robot, const uint32_t* key8, uint
   CUDA_TRY(optik_launch_chacha8_kat((const uint32_t*)buf.p, stream_id, (uint32_t*)(buf.p + 128), robot->stream));
   CUDA_TRY(cudaMemcpyAsync(words16_out, buf.p + 128, 64, cudaMemcpyDeviceToHost, robot->stream));
   CUDA_TRY(cudaStreamSynchronize(robot->stream));
+  return OPTIK_OK;
+}
+
+uint64_t optik_gpu_exchange_bytes(const optik_robot* robot, uint32_t world) {
+  if (!robot || world == 0) return 0;
+  const uint64_t len = OPTIK_RECORD_HEAD + (uint64_t)robot->n;
+  return (uint64_t)optik_exchange_nslot() * world * (len * sizeof(double) + sizeof(uint64_t));
+}
+int optik_gpu_exchange_push(const optik_robot* robot, const double* record, const uint64_t* peer_buffers_dev, uint32_t rank,
+                            uint32_t world, uint64_t seq, void* stream) {
+  if (!robot || !record || !peer_buffers_dev || world == 0 || world > 32 || rank >= world || seq == 0)
+    return fail(OPTIK_ERR_INVALID, "bad exchange arguments (1 <= world <= 32, rank < world, seq >= 1)");
+  CUDA_TRY(cudaSetDevice(robot->device));
+  CUDA_TRY(optik_launch_exchange_push(record, OPTIK_RECORD_HEAD + robot->n, peer_buffers_dev, (int)rank, (int)world, seq, stream));
+  return OPTIK_OK;
+}
+int optik_gpu_exchange_select(const optik_robot* robot, const double* local_buffer, uint32_t world, uint64_t seq,
+                              double* best_record_out, void* stream) {
+  if (!robot || !local_buffer || !best_record_out || world == 0 || world > 32 || seq == 0)
+    return fail(OPTIK_ERR_INVALID, "bad exchange arguments (1 <= world <= 32, seq >= 1)");
+  CUDA_TRY(cudaSetDevice(robot->device));
+  CUDA_TRY(optik_launch_exchange_select(local_buffer, (int)world, robot->n, seq, best_record_out, stream));
   return OPTIK_OK;
 }
 

@@ -66,11 +66,60 @@ def all_gather_records(record, group=None, out=None):
     return out
 
 
+class PeerExchange:
+    """The best-pick exchange as direct peer-to-peer stores over NVLink (optik_gpu_exchange_push / _select,
+    csrc/exchange_kernel.cu) instead of an NCCL all-gather: every rank owns one symmetric buffer that torch's symmetric
+    memory maps into every peer (plumbing: allocation + handle exchange only; the data path is our two kernels).
+    `PeerExchange.create` returns None where peer mapping is unavailable (callers then use the NCCL all-gather)."""
+
+    def __init__(self, robot, rank, world, group, device):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import load_library, _check
+        self._lib, self._check, self.robot, self.rank, self.world = load_library(), _check, robot, rank, world
+        nbytes = int(self._lib.optik_gpu_exchange_bytes(robot._h, world))
+        self.buf = symm.empty(nbytes // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        grp = group if group is not None else dist.group.WORLD
+        self.handle = symm.rendezvous(self.buf, grp.group_name if hasattr(grp, "group_name") else grp)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == world and ptrs[rank] == self.buf.data_ptr()
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)  # device array of the peers' base addresses
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every buffer is zeroed before anybody pushes
+
+    @staticmethod
+    def create(robot, rank, world, group=None, device=None):
+        import torch
+        try:
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            return PeerExchange(robot, rank, world, group, dev)
+        except Exception as e:  # no peer access / symmetric memory on this system
+            import sys
+            print(f"optik_b200.dist: peer-to-peer exchange unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+            return None
+
+    def exchange(self, record, out):
+        """Enqueue push + select on the current stream: `record` (this rank's candidate) -> `out` (the global best)."""
+        import torch
+        self.seq += 1
+        stream = torch.cuda.current_stream(record.device).cuda_stream
+        self._check(self._lib.optik_gpu_exchange_push(self.robot._h, record.data_ptr(), self.peers.data_ptr(), self.rank,
+                                                      self.world, self.seq, stream))
+        self._check(self._lib.optik_gpu_exchange_select(self.robot._h, self.buf.data_ptr(), self.world, self.seq,
+                                                        out.data_ptr(), stream))
+        return out
+
+
 def ik_restart_sharded(robot, config, target, x0, restarts_per_rank, rank=0, world=1, group=None, tile=0,
-                       counters=None, out=None, record=None, gathered=None, best=None):
+                       counters=None, out=None, record=None, gathered=None, best=None, exchange=None):
     """One target, restarts sharded over ranks: rank g runs [g*R, (g+1)*R), selects its best candidate on the
     device (select_kernel), ONE all-gather of the candidate record, then the same selection rule over the gathered
-    records (optik_gpu_select_records) gives every rank the GLOBAL best under config.solution_mode.
+    records (optik_gpu_select_records) gives every rank the GLOBAL best under config.solution_mode.  With
+    `exchange` (a PeerExchange) the all-gather is replaced by direct peer-to-peer stores + a flag wait.
     Returns (best_record, local_records); everything stays on the device, no host sync.
     target (8,), x0 (n,) CUDA float64 tensors; record/gathered/best are optional preallocated buffers."""
     R = int(restarts_per_rank)
@@ -78,6 +127,11 @@ def ik_restart_sharded(robot, config, target, x0, restarts_per_rank, rank=0, wor
                                           counters=counters, out=out, record=record)
     if world == 1:
         return rec, (q, f, st, ev)
+    if exchange is not None:  # direct peer stores over NVLink + a flag wait
+        import torch
+        if best is None:
+            best = torch.empty_like(rec)
+        return exchange.exchange(rec, best), (q, f, st, ev)
     allrec = all_gather_records(rec, group, out=gathered)
     return robot.select_records(allrec, out=best), (q, f, st, ev)
 
@@ -105,8 +159,11 @@ class HostStepPipeline:
     candidate record -> select_records -> D2H of this rank's per-restart records and of the global best record.
     Nothing blocks the host until result(slot).  With world == 1 the all-gather is skipped."""
 
-    def __init__(self, robot, config, restarts_per_rank, rank=0, world=1, group=None, tile=0, depth=2, device=None):
+    def __init__(self, robot, config, restarts_per_rank, rank=0, world=1, group=None, tile=0, depth=2, device=None,
+                 exchange=None):
         import torch
+        assert exchange is None or depth <= 4, "the peer exchange keeps at most 4 calls in flight"
+        self.exchange = exchange
         self.robot, self.config, self.R, self.rank, self.world, self.group, self.tile = robot, config, int(restarts_per_rank), rank, world, group, tile
         n = robot.num_positions()
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -139,7 +196,7 @@ class HostStepPipeline:
             s["d_in"][1].copy_(s["h_in"][1], non_blocking=True)
             best, _ = ik_restart_sharded(self.robot, self.config, s["d_in"][0], s["d_in"][1], self.R, rank=self.rank,
                                          world=self.world, group=self.group, tile=self.tile, out=s["d_out"],
-                                         record=s["record"], gathered=s["gathered"], best=s["best"])
+                                         record=s["record"], gathered=s["gathered"], best=s["best"], exchange=self.exchange)
             for h, dv in zip(s["h_out"], s["d_out"]):
                 h.copy_(dv, non_blocking=True)
             s["h_best"].copy_(best, non_blocking=True)

@@ -842,3 +842,41 @@ def test_solve_against_slsqp_standin(name, R):
           f"same-start polish max |dq| {max(same_start):.2e} rad over {len(same_start)}; "
           f"same-branch rate {branch / max(len(sample), 1):.2f}, own-start polish max |dq| "
           f"{max(own_start) if own_start else float('nan'):.2e} rad")
+
+
+def test_peer_exchange_kernels_single_gpu():
+    """optik_gpu_exchange_push / _select (the NVLink best-pick exchange) with four simulated ranks on one GPU: each
+    'rank' owns a buffer, every push lands in every buffer, every select returns the record the torch specification of
+    the rule (dist.select_candidates) picks; sequence numbers reuse the 8 slots; a missing peer times out as found=-1."""
+    import torch
+    from optik_b200 import dist as obd
+    r, ch = robot_and_chain("panda")
+    lib = ob.load_library()
+    W, n = 4, ch.n
+    L = obd.RECORD_HEAD + n
+    nbytes = int(lib.optik_gpu_exchange_bytes(r._h, W))
+    assert nbytes == 8 * W * (L * 8 + 8)
+    bufs = [torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda") for _ in range(W)]
+    peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    rng = np.random.default_rng(3)
+    stream = torch.cuda.current_stream().cuda_stream
+    for seq in range(1, 20):
+        recs = []
+        for w in range(W):
+            found = float(rng.random() < 0.7)
+            rec = obd.pack_candidate(found, float(rng.integers(0, 3)), float(rng.integers(0, 5)), 1e-7,
+                                     torch.from_numpy(rng.uniform(-1, 1, n)).cuda())
+            recs.append(rec)
+            ob._check(lib.optik_gpu_exchange_push(r._h, rec.data_ptr(), peers.data_ptr(), w, W, seq, stream))
+        ref = obd.select_candidates(torch.stack(recs), as_tensor=True)
+        for w in range(W):
+            out = torch.empty(L, dtype=torch.float64, device="cuda")
+            ob._check(lib.optik_gpu_exchange_select(r._h, bufs[w].data_ptr(), W, seq, out.data_ptr(), stream))
+            assert torch.equal(out, ref), (seq, w)
+    # only three of four ranks push sequence 20: the select gives up after its bounded wait
+    for w in range(3):
+        ob._check(lib.optik_gpu_exchange_push(r._h, recs[w].data_ptr(), peers.data_ptr(), w, W, 20, stream))
+    out = torch.empty(L, dtype=torch.float64, device="cuda")
+    ob._check(lib.optik_gpu_exchange_select(r._h, bufs[0].data_ptr(), W, 20, out.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert out[0].item() == -1.0
