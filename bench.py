@@ -696,8 +696,8 @@ def run_product(args):
                             "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
                             "the records and the global best, all on the pass's stream; %d passes in flight" % E2E_DEPTH_MULTI),
                     "blocking_call_value": sync_conv / sync_s, "blocking_call_ms_median": float(np.median(sync_times) * 1e3)},
-            # per pass: seed_table + solve_t1 + select (slice pass + final pass) [+ exchange push + select | select_records]
-            "gpu_launches": (4 if world == 1 else (6 if px is not None else 5)) * NP,
+            # per pass: solve_t1 (selection fused; the seed table is cached per robot) [+ exchange select | ncclAllGather + select_records]
+            "gpu_launches": (1 if world == 1 else (2 if px is not None else 3)) * NP,
             "exchange": (None if world == 1 else "peer-to-peer stores over NVLink (optik_gpu_exchange_push/_select)" if px is not None
                          else "ncclAllGather + optik_gpu_select_records"),
             "roofline": roof,

@@ -157,6 +157,12 @@ typedef struct optik_gpu_batch_opts {
   uint32_t flags;          /* OPTIK_BATCH_* bits */
   uint32_t variant;        /* thread-per-seed kernel: 0 = default, 1 = trial columns in local memory (3 blocks/SM),
                               2 = in shared memory (2 blocks/SM); same results bit for bit */
+  /* optik_gpu_ik_attempts with best_record_out, device memory, thread-per-seed kernel: the launch that writes the
+   * candidate record also stores it into every peer's exchange buffer (see optik_gpu_exchange_push: same arguments,
+   * no extra launch).  push_peers = NULL: off. */
+  const uint64_t* push_peers;
+  uint32_t push_rank, push_world;
+  uint64_t push_seq;
 } optik_gpu_batch_opts;
 
 /* opts->flags.  OPTIK_BATCH_ASYNC (host-memory calls only, `stream` must be non-NULL): enqueue the H2D copies, the

@@ -40,7 +40,8 @@ class _BatchOpts(C.Structure):  # == optik_gpu_batch_opts
                 ("chunks", C.c_uint32), ("tile", C.c_uint32), ("max_evals", C.c_uint32), ("blocks", C.c_uint32),
                 ("memory", C.c_int32), ("ee_offset", C.c_void_p), ("restart_out", C.c_void_p),
                 ("evals_out", C.c_void_p), ("counters", C.c_void_p), ("best_record_out", C.c_void_p),
-                ("flags", C.c_uint32), ("variant", C.c_uint32)]
+                ("flags", C.c_uint32), ("variant", C.c_uint32), ("push_peers", C.c_void_p), ("push_rank", C.c_uint32),
+                ("push_world", C.c_uint32), ("push_seq", C.c_uint64)]
 
 
 BATCH_ASYNC, BATCH_STATIC = 1, 8  # == OPTIK_BATCH_*
@@ -509,7 +510,7 @@ class Robot:
         return (q, f, st, extra) if stats else (q, f, st)
 
     def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None,
-                    best=False, out=None, counters=None, record=None, stream=None, wait=True, variant=0):
+                    best=False, out=None, counters=None, record=None, stream=None, wait=True, variant=0, push=None):
         """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
         completion (no Speed-mode early exit) -- BASELINE config 2's output.  best=True also runs the selection
         pass (lib.rs:397-413) and appends the packed candidate record (RECORD_HEAD + n doubles:
@@ -535,6 +536,8 @@ class Robot:
                 if record is None:
                     record = torch.empty((RECORD_HEAD + n,), dtype=torch.float64, device=dev)
                 o.best_record_out = record.data_ptr()
+            if push is not None:  # (peers device array ptr, rank, world, seq): fused store into the peers' exchange buffers
+                o.push_peers, o.push_rank, o.push_world, o.push_seq = int(push[0]), int(push[1]), int(push[2]), int(push[3])
             if counters is not None:
                 o.counters = counters.data_ptr()
             stream = torch.cuda.current_stream(dev).cuda_stream

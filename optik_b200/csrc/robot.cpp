@@ -154,9 +154,15 @@ struct optik_robot {
   mutable cudaMemPool_t pool = nullptr;  // library-owned stream-ordered pool (the process's default pool is left alone)
   mutable DevBuf key_dev;                // ChaCha8 key = seed_from_u64(42), 8 words
   mutable DevBuf seed_cache;             // restart seeds for indices [0, SEED_CACHE) (lib.rs:360-370)
+  // the first long restart range a caller asks for (e.g. a rank's 65 536 restarts) keeps its seed table too
+  mutable std::mutex seed_mu;
+  mutable DevBuf seed_big;
+  mutable uint64_t seed_big_begin = 0, seed_big_count = 0;
+  mutable cudaEvent_t seed_big_ready = nullptr;
 
   ~optik_robot() {
     if (stream) cudaStreamDestroy(stream);
+    if (seed_big_ready) cudaEventDestroy(seed_big_ready);
     if (pinned) cudaFreeHost(pinned);
     if (pool) cudaMemPoolDestroy(pool);
   }
@@ -399,7 +405,9 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   unsigned help_cap = 1;
   if (dyn) while (help_cap < 4u * (unsigned)plan0.resident_tiles) help_cap <<= 1;
   const size_t dyn_zero = 384 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned);
-  const size_t off_zero = carve(dyn ? dyn_zero : sizeof(unsigned long long));
+  const size_t off_zero = carve(dyn ? dyn_zero : 16);  // static: [queue (8 B) | fused_done (4 B)]
+  const bool fused = tile == 1 && per_attempt_records && T == 1 && d_best_record != nullptr;  // selection inside the solve launch
+  const size_t off_fpart = fused ? carve((size_t)plan.blocks * 24) : 0;
   const size_t off_dfound = dyn ? carve(T * sizeof(unsigned)) : 0;
   // selection: slice the candidate range when one target has very many chunks
   unsigned slices = 1;
@@ -412,8 +420,22 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     if (r_begin + R <= SEED_CACHE || R > SEED_TABLE_MAX) {
       P.seed_tab = (const double*)r->seed_cache.p; P.seed_begin = 0; P.seed_count = SEED_CACHE;
     } else {
-      own_table = true;
-      off_seed = carve((size_t)R * n * sizeof(double));
+      std::lock_guard<std::mutex> lk(r->seed_mu);
+      if (r->seed_big_count == 0) {  // first long range of this robot: build its table once, on this stream
+        if (r->seed_big.reserve((size_t)R * n * sizeof(double)) == 0 &&
+            cudaEventCreateWithFlags(&r->seed_big_ready, cudaEventDisableTiming) == cudaSuccess) {
+          CUDA_TRY(optik_launch_seed_table(P.chain, n, (const uint32_t*)r->key_dev.p, r_begin, R, (double*)r->seed_big.p, s));
+          CUDA_TRY(cudaEventRecord(r->seed_big_ready, s));
+          r->seed_big_begin = r_begin; r->seed_big_count = R;
+        }
+      }
+      if (r->seed_big_count && r_begin >= r->seed_big_begin && r_begin + R <= r->seed_big_begin + r->seed_big_count) {
+        CUDA_TRY(cudaStreamWaitEvent(s, r->seed_big_ready, 0));
+        P.seed_tab = (const double*)r->seed_big.p; P.seed_begin = r->seed_big_begin; P.seed_count = r->seed_big_count;
+      } else {
+        own_table = true;
+        off_seed = carve((size_t)R * n * sizeof(double));
+      }
     }
   }
   StreamBuf scratch;
@@ -447,7 +469,19 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     if (d_evals) CUDA_TRY(cudaMemsetAsync(d_evals, 0, T * sizeof(int32_t), s));
   } else {
     P.sched = (per_attempt_records && tile == 1 && T == 1) ? 2 : 0;
-    CUDA_TRY(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(P.queue, 0, 16, s));
+    if (fused) {
+      P.fused_record = d_best_record;
+      P.fused_done = (unsigned*)(sc + off_zero + 8);
+      P.fused_part_score = (double*)(sc + off_fpart);
+      P.fused_part_restart = (unsigned long long*)(sc + off_fpart + (size_t)plan.blocks * 8);
+      P.fused_part_has = (int*)(sc + off_fpart + (size_t)plan.blocks * 16);
+      if (o && o->push_peers) {
+        if (o->push_world == 0 || o->push_world > 32 || o->push_rank >= o->push_world || o->push_seq == 0)
+          return fail(OPTIK_ERR_INVALID, "bad exchange arguments in opts (1 <= push_world <= 32, push_rank < push_world, push_seq >= 1)");
+        P.push_peers = o->push_peers; P.push_rank = (int)o->push_rank; P.push_world = (int)o->push_world; P.push_seq = o->push_seq;
+      }
+    }
     if (use_found) {
       P.found = (unsigned long long*)(sc + off_found);
       CUDA_TRY(cudaMemsetAsync(P.found, 0xff, T * sizeof(unsigned long long), s));
@@ -460,7 +494,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   }
   if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, (P.has_prismatic || P.weighted) ? 1 : 0, rows, plan.blocks, s));
   else CUDA_TRY(optik_launch_solve(&P, plan.tile, plan.blocks, s));
-  if (per_attempt_records && d_best_record) {  // selection pass over the per-attempt records -> one packed record
+  if (per_attempt_records && d_best_record && !fused) {  // selection pass over the per-attempt records -> one packed record
     SelectParams S{};
     S.T = 1; S.C = P.C; S.n = n; S.mode = cfg->solution_mode;
     S.cand_q = P.cand_q; S.cand_f = P.cand_f; S.cand_score = P.cand_score; S.cand_restart = P.cand_restart;

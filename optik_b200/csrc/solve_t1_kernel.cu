@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
   unsigned n_attempts = 0, n_evals = 0, n_conv = 0;
 
+  int sel_has = -1;  // sched 2 with a fused selection: this lane's best attempt (converged?, score, restart index)
+  double sel_score = 0.0;
+  unsigned long long sel_restart = ~0ull;
   unsigned pass = 0;  // warp-uniform loop counter
   for (;;) {
     pass++;
@@ -473,6 +476,13 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
           if (sched == 2) P.cand_evals[job] = evals;
         }
+        if (sched == 2 && P.fused_record) {  // this lane's best attempt so far, for the in-kernel selection pass
+          const int has = success ? 1 : 0;
+          const double sc = speed ? (double)r_idx : score;  // Speed: lowest converged index (lib.rs:409-412)
+          if (has > sel_has || (has == sel_has && (sc < sel_score || (sc == sel_score && r_idx < sel_restart)))) {
+            sel_has = has; sel_score = sc; sel_restart = r_idx;
+          }
+        }
         if (success) {
           if (record) { best_has = true; best_score = score; }
           if (speed && sched == 0) {  // first success ends the chunk (lib.rs:381-387, 411)
@@ -591,6 +601,90 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       const double Jm[6] = {m * a0.x, m * a0.y, m * a1.x, m * a1.y, m * a2.x, m * a2.y};
       const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
       qt_[j * T1_THREADS] = fmin(fmax(qc[j * T1_THREADS] - dot6(Jm, y), jc[12]), jc[13]);
+    }
+  }
+
+  // ---------------- fused selection (lib.rs:397-413) for per-attempt launches: lane -> warp -> block -> the last block
+  // to finish reduces the per-block winners and writes the ONE candidate record (and, across GPUs, stores it straight
+  // into every peer's exchange buffer over NVLink: csrc/exchange_kernel.cu's push without its launch)
+  if (sched == 2 && P.fused_record) {
+    __shared__ int s_has[T1_THREADS / 32 + 1];
+    __shared__ double s_score[T1_THREADS / 32 + 1];
+    __shared__ unsigned long long s_restart[T1_THREADS / 32 + 1];
+    __shared__ bool s_last;
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int h2 = __shfl_xor_sync(FULLMASK, sel_has, o);
+      const double c2 = __shfl_xor_sync(FULLMASK, sel_score, o);
+      const unsigned long long r2 = __shfl_xor_sync(FULLMASK, sel_restart, o);
+      if (h2 > sel_has || (h2 == sel_has && (c2 < sel_score || (c2 == sel_score && r2 < sel_restart)))) {
+        sel_has = h2; sel_score = c2; sel_restart = r2;
+      }
+    }
+    if (lane == 0) { s_has[tid >> 5] = sel_has; s_score[tid >> 5] = sel_score; s_restart[tid >> 5] = sel_restart; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < T1_THREADS / 32; w++)
+        if (s_has[w] > sel_has || (s_has[w] == sel_has && (s_score[w] < sel_score || (s_score[w] == sel_score && s_restart[w] < sel_restart)))) {
+          sel_has = s_has[w]; sel_score = s_score[w]; sel_restart = s_restart[w];
+        }
+      P.fused_part_has[blockIdx.x] = sel_has; P.fused_part_score[blockIdx.x] = sel_score; P.fused_part_restart[blockIdx.x] = sel_restart;
+      __threadfence();  // this block's records and its partial are visible before it counts as finished
+      s_last = atomicAdd(P.fused_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      int h = -1;
+      double sc = 0.0;
+      unsigned long long rs = ~0ull;
+      for (unsigned b = tid; b < gridDim.x; b += T1_THREADS) {
+        const int h2 = ((volatile int*)P.fused_part_has)[b];
+        const double c2 = ((volatile double*)P.fused_part_score)[b];
+        const unsigned long long r2 = ((volatile unsigned long long*)P.fused_part_restart)[b];
+        if (h2 > h || (h2 == h && (c2 < sc || (c2 == sc && r2 < rs)))) { h = h2; sc = c2; rs = r2; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int h2 = __shfl_xor_sync(FULLMASK, h, o);
+        const double c2 = __shfl_xor_sync(FULLMASK, sc, o);
+        const unsigned long long r2 = __shfl_xor_sync(FULLMASK, rs, o);
+        if (h2 > h || (h2 == h && (c2 < sc || (c2 == sc && r2 < rs)))) { h = h2; sc = c2; rs = r2; }
+      }
+      __syncthreads();
+      if (lane == 0) { s_has[tid >> 5] = h; s_score[tid >> 5] = sc; s_restart[tid >> 5] = rs; }
+      __syncthreads();
+      if (tid < 32) {  // warp 0 finishes and writes the record [found, score, restart, cost, status, 0,0,0, q...]
+        h = s_has[0]; sc = s_score[0]; rs = s_restart[0];
+        for (int w = 1; w < T1_THREADS / 32; w++)
+          if (s_has[w] > h || (s_has[w] == h && (s_score[w] < sc || (s_score[w] == sc && s_restart[w] < rs)))) {
+            h = s_has[w]; sc = s_score[w]; rs = s_restart[w];
+          }
+        const unsigned long long win = (h >= 0) ? rs - P.r_begin : 0ull;  // job index of the winning attempt
+        const int len = 8 + n;
+        double v = 0.0;
+        if (tid == 0) v = h > 0 ? 1.0 : 0.0;
+        else if (tid == 1) v = speed ? (double)rs : ((volatile double*)P.cand_score)[win];
+        else if (tid == 2) v = (double)rs;
+        else if (tid == 3) v = ((volatile double*)P.cand_f)[win];
+        else if (tid == 4) v = (double)((volatile int*)P.cand_status)[win];
+        else if (tid >= 8 && tid < len) v = ((volatile double*)P.cand_q)[win * n + (tid - 8)];
+        if (tid < len) P.fused_record[tid] = v;
+        if (P.push_peers) {  // cross-GPU: row `push_rank` of slot push_seq % 8 in every peer's buffer, then its flag
+          const unsigned slot = (unsigned)(P.push_seq % 8ull);
+          for (int p = 0; p < P.push_world; p++) {
+            double* base = (double*)P.push_peers[p];
+            if (tid < len) base[((size_t)slot * P.push_world + P.push_rank) * len + tid] = v;
+          }
+          __threadfence_system();
+          __syncwarp();
+          if (tid < P.push_world) {
+            unsigned long long* flags = (unsigned long long*)((double*)P.push_peers[tid] + (size_t)8 * P.push_world * len);
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags + (size_t)slot * P.push_world + P.push_rank), "l"(P.push_seq) : "memory");
+          }
+        }
+      }
     }
   }
 

@@ -84,6 +84,17 @@ struct SolveParams {
   unsigned long long* dyn_ctl;        // [0] ticket head [1] ticket tail [2] live chains     (zeroed)
   unsigned* help_slots;               // [help_mask + 1] ticket ring, value = target + 1     (zeroed)
   unsigned help_mask;
+  // thread-per-seed kernel, sched = 2: selection fused into the solve launch (last block done).  fused_record = the
+  // packed candidate record [8 + n]; partials are per block; fused_done is zeroed by the host.
+  double* fused_record;
+  int* fused_part_has;
+  double* fused_part_score;
+  unsigned long long* fused_part_restart;
+  unsigned* fused_done;
+  // optional: the last block also stores the record into every peer's exchange buffer (csrc/exchange_kernel.cu layout)
+  const uint64_t* push_peers;         // device array of push_world base addresses, or null
+  int push_rank, push_world;
+  unsigned long long push_seq;
 };
 
 namespace optik { struct SelKey; }

@@ -109,7 +109,17 @@ class PeerExchange:
         stream = torch.cuda.current_stream(record.device).cuda_stream
         self._check(self._lib.optik_gpu_exchange_push(self.robot._h, record.data_ptr(), self.peers.data_ptr(), self.rank,
                                                       self.world, self.seq, stream))
-        self._check(self._lib.optik_gpu_exchange_select(self.robot._h, self.buf.data_ptr(), self.world, self.seq,
+        return self.select(out, self.seq)
+
+    def next_push(self):
+        """Arguments for a solve launch that pushes its candidate record itself (Robot.ik_attempts(push=...))."""
+        self.seq += 1
+        return (self.peers.data_ptr(), self.rank, self.world, self.seq)
+
+    def select(self, out, seq):
+        import torch
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        self._check(self._lib.optik_gpu_exchange_select(self.robot._h, self.buf.data_ptr(), self.world, int(seq),
                                                         out.data_ptr(), stream))
         return out
 
@@ -123,14 +133,18 @@ def ik_restart_sharded(robot, config, target, x0, restarts_per_rank, rank=0, wor
     Returns (best_record, local_records); everything stays on the device, no host sync.
     target (8,), x0 (n,) CUDA float64 tensors; record/gathered/best are optional preallocated buffers."""
     R = int(restarts_per_rank)
+    fused_push = exchange is not None and world > 1 and tile in (0, 1) and robot.num_positions() <= 8
+    push = exchange.next_push() if fused_push else None
     q, f, st, ev, rec = robot.ik_attempts(config, target, x0, R, restart_begin=rank * R, tile=tile, best=True,
-                                          counters=counters, out=out, record=record)
+                                          counters=counters, out=out, record=record, push=push)
     if world == 1:
         return rec, (q, f, st, ev)
-    if exchange is not None:  # direct peer stores over NVLink + a flag wait
+    if exchange is not None:  # direct peer stores over NVLink (by the solve launch itself when it can) + a flag wait
         import torch
         if best is None:
             best = torch.empty_like(rec)
+        if fused_push:
+            return exchange.select(best, push[3]), (q, f, st, ev)
         return exchange.exchange(rec, best), (q, f, st, ev)
     allrec = all_gather_records(rec, group, out=gathered)
     return robot.select_records(allrec, out=best), (q, f, st, ev)
