@@ -18,6 +18,7 @@
 #include <random>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/optik_b200.h"
@@ -132,6 +133,20 @@ struct DevBuf {  // grow-only device scratch
 
 }  // namespace
 
+// One in-flight Robot::ik() call: its own stream, persistent device scratch (control words + one wave of candidate
+// records) and a mapped pinned host block the kernel reads its inputs from and writes its result + completion flag to.
+constexpr int IK_SLOTS = 8;
+constexpr uint64_t IK_WAVE = 256;  // restarts per launch of a single-target call
+struct IkSlot {
+  std::atomic<bool> busy{false};
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  char* dev = nullptr;       // [queue 8 | fused_done 8 | found 8 | pad] then the candidate arrays
+  double* host = nullptr;    // mapped: [0..7] target, [8..40) x0, [64..64+8+n) record, [128] completion flag
+  double* host_dev = nullptr;
+  unsigned long long seq = 0;
+};
+
 struct optik_robot {
   std::vector<optik::Joint> joints;  // articulated joints, then at most one fixed tip joint
   int n = 0;                         // num_positions
@@ -159,10 +174,16 @@ struct optik_robot {
   mutable DevBuf seed_big;
   mutable uint64_t seed_big_begin = 0, seed_big_count = 0;
   mutable cudaEvent_t seed_big_ready = nullptr;
+  mutable IkSlot ik_slots[IK_SLOTS];
 
   ~optik_robot() {
     if (stream) cudaStreamDestroy(stream);
     if (seed_big_ready) cudaEventDestroy(seed_big_ready);
+    for (IkSlot& sl : ik_slots) {
+      if (sl.stream) cudaStreamDestroy(sl.stream);
+      if (sl.dev) cudaFree(sl.dev);
+      if (sl.host) cudaFreeHost(sl.host);
+    }
     if (pinned) cudaFreeHost(pinned);
     if (pool) cudaMemPoolDestroy(pool);
   }
@@ -917,40 +938,73 @@ int optik_gpu_ik_attempts(const optik_robot* robot, const optik_solver_config* c
 }  // extern "C"
 
 // ---------------------------------------------------------------- Robot::ik (single target), lib.rs:241-415
+// One call = waves of IK_WAVE restarts, ONE kernel launch per wave and nothing else on the critical path: the kernel reads
+// target and seed from mapped pinned host memory, its last block selects the winner (lib.rs:397-413), writes the record
+// back into mapped memory and raises a flag the host polls.  Up to IK_SLOTS calls run concurrently on one Robot (the
+// reference's ik() takes &self and may be called from many threads): each takes a slot with its own stream and scratch.
 // Returns 1 and fills q_out/cost_out when a restart converged, 0 for "no solution" (== None), <0 = -(error code).
+static int ik_slot_init(const optik_robot* robot, IkSlot& sl) {
+  const int n = robot->n;
+  const size_t W = IK_WAVE;
+  const size_t bytes = 256 + W * (n * 8 + 8 + 8 + 8 + 4 + 4) + 256;
+  CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc((void**)&sl.dev, bytes));
+  CUDA_TRY(cudaMemset(sl.dev, 0, bytes));
+  CUDA_TRY(cudaMemset(sl.dev + 16, 0xff, 8));  // found[0] = ~0
+  CUDA_TRY(cudaHostAlloc((void**)&sl.host, 2048, cudaHostAllocMapped));
+  memset(sl.host, 0, 2048);
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&sl.host_dev, sl.host, 0));
+  CUDA_TRY(cudaDeviceSynchronize());  // the memsets ran on the default stream; the slot's stream does not wait for it
+  sl.ready = true;
+  return OPTIK_OK;
+}
+
 static int ik_single(const optik_robot* robot, const optik_solver_config* config, const double* tgt8, const double* x0,
                      const double* ee_offset, double* q_out, double* cost_out) {
   const int n = robot->n;
   if (int rc = check_seeds_host(robot, x0, 1)) return -rc;
-  std::lock_guard<std::mutex> lk(robot->mu);
-  if (int rc = robot->ensure_gpu()) return -rc;
+  {
+    std::lock_guard<std::mutex> lk(robot->mu);
+    if (int rc = robot->ensure_gpu()) return -rc;
+  }
   if (cudaSetDevice(robot->device) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaSetDevice failed");
   // max_time (lib.rs:260-264) runs from here: the one-time device initialisation of a fresh Robot is not solve time
   const auto t_begin = std::chrono::steady_clock::now();
-  cudaStream_t s = robot->stream;
-  const int tile = choose_tile(n, 0, false);  // single target: the low-latency tile layout
-  const Plan plan = make_plan(robot, tile, 2, 0, ~0ull);
-  const uint64_t wave = (uint64_t)plan.resident_tiles;                                    // restarts per launch
-  const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
-  const size_t o_t = 0, o_x = 64, o_q = o_x + ((n * 8 + 255) & ~255), o_f = o_q + ((n * 8 + 255) & ~255), o_s = o_f + 256,
-               total = o_s + 256;
-  if (robot->scratch.reserve(total)) return -fail(OPTIK_ERR_CUDA, "cudaMalloc failed");
-  char* d = (char*)robot->scratch.p;
-  if (!robot->pinned) {
-    if (cudaMallocHost(&robot->pinned, 4096) != cudaSuccess) return -fail(OPTIK_ERR_CUDA, "cudaMallocHost failed");
-    robot->pinned_cap = 4096;
+  // ---- take a slot (calls beyond IK_SLOTS wait for one)
+  IkSlot* sl = nullptr;
+  for (;;) {
+    for (IkSlot& c : robot->ik_slots)
+      if (!c.busy.exchange(true, std::memory_order_acquire)) { sl = &c; break; }
+    if (sl) break;
+    std::this_thread::yield();
   }
-  double* h = (double*)robot->pinned;  // [0..7] target, [8..8+n) x0, [64..64+n) q, [100] f, [101] status
-  memcpy(h, tgt8, 64);
-  memcpy(h + 8, x0, n * 8);
-  if (cudaMemcpyAsync(d + o_t, h, 64, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-      cudaMemcpyAsync(d + o_x, h + 8, n * 8, cudaMemcpyHostToDevice, s) != cudaSuccess)
-    return -fail(OPTIK_ERR_CUDA, "H2D copy failed");
-  optik_gpu_batch_opts o{};
-  o.struct_size = sizeof(o);
-  o.memory = 1;
-  o.tile = (uint32_t)tile;
-  o.ee_offset = ee_offset;
+  struct Release { IkSlot* s; ~Release() { s->busy.store(false, std::memory_order_release); } } release{sl};
+  if (!sl->ready)
+    if (int rc = ik_slot_init(robot, *sl)) return -rc;
+  const int tile = choose_tile(n, 0, false);  // single target: the low-latency tile layout, one restart per tile
+  const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
+  const bool speed = config->solution_mode == OPTIK_MODE_SPEED;
+  SolveParams P{};
+  fill_common(robot, config, ee_offset, 0, P);
+  volatile double* h = sl->host;
+  for (int i = 0; i < 8; i++) h[i] = tgt8[i];
+  for (int i = 0; i < n; i++) h[8 + i] = x0[i];
+  P.targets = sl->host_dev; P.x0 = sl->host_dev + 8; P.T = 1;
+  char* d = sl->dev;
+  P.queue = (unsigned long long*)d;
+  P.fused_done = (unsigned*)(d + 8);
+  P.found = speed ? (unsigned long long*)(d + 16) : nullptr;
+  const size_t W = IK_WAVE;
+  P.cand_q = (double*)(d + 256);
+  P.cand_f = P.cand_q + W * n;
+  P.cand_score = P.cand_f + W;
+  P.cand_restart = (unsigned long long*)(P.cand_score + W);
+  P.cand_status = (int*)(P.cand_restart + W);
+  P.cand_evals = P.cand_status + W;
+  P.fused_record = sl->host_dev + 64;
+  P.fused_flag = (unsigned long long*)(sl->host_dev + 128);
+  P.fused_reset = 1;
+  volatile unsigned long long* flag = (volatile unsigned long long*)(sl->host + 128);
   bool have_best = false;
   double best_score = 0;
   uint64_t done = 0;
@@ -965,28 +1019,39 @@ static int ik_single(const optik_robot* robot, const optik_solver_config* config
         remaining = 1e-6;  // at least one wave runs (restart 0 is evaluated once before its deadline check)
       }
     }
-    const uint64_t R = (max_restarts - done) < wave ? (max_restarts - done) : wave;
-    const unsigned long long max_ns = config->max_time > 0.0 ? (unsigned long long)(remaining * 1e9) + 1 : 0ull;
-    if (int rc = solve_device(robot, config, &o, (double*)(d + o_t), (double*)(d + o_x), 1, done, R, (double*)(d + o_q),
-                              (double*)(d + o_f), (int32_t*)(d + o_s), nullptr, nullptr, nullptr, max_ns, false, s))
-      return -rc;
-    if (cudaMemcpyAsync(h + 64, d + o_q, n * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(h + 100, d + o_f, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(h + 101, d + o_s, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess)
-      return -fail(OPTIK_ERR_CUDA, std::string("ik: ") + cudaGetErrorString(cudaGetLastError()));
+    const uint64_t R = (max_restarts - done) < W ? (max_restarts - done) : W;
+    P.r_begin = done; P.r_end = done + R; P.C = (uint32_t)R;
+    P.max_ns = config->max_time > 0.0 ? (unsigned long long)(remaining * 1e9) + 1 : 0ull;
+    P.fused_seq = ++sl->seq;
+    const int tiles_per_block = 128 / tile;
+    const int blocks = (int)((R + tiles_per_block - 1) / tiles_per_block);
+    if (int e = optik_launch_solve(&P, tile, blocks, sl->stream))
+      return -fail(OPTIK_ERR_CUDA, std::string("ik launch: ") + cudaGetErrorString((cudaError_t)e));
+    // poll the completion flag in mapped memory (a stream synchronisation costs several microseconds more)
+    const auto t_wait = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*flag != P.fused_seq) {
+      if ((++spins & 0x3ff) == 0) {
+        if (cudaStreamQuery(sl->stream) != cudaErrorNotReady && *flag != P.fused_seq) {  // finished without a flag: an error
+          const cudaError_t e = cudaStreamSynchronize(sl->stream);
+          if (*flag == P.fused_seq) break;
+          return -fail(OPTIK_ERR_CUDA, std::string("ik: ") + cudaGetErrorString(e == cudaSuccess ? cudaGetLastError() : e));
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count() > 30.0)
+          return -fail(OPTIK_ERR_CUDA, "ik: kernel did not complete within 30 s");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     done += R;
-    int32_t st;
-    memcpy(&st, h + 101, 4);
-    if (optik_status_is_success(config, st)) {
+    if (h[64] > 0.0) {  // a restart of this wave converged: record = [found, score, restart, cost, status, 0,0,0, q...]
       double score = 0;
-      for (int i = 0; i < n; i++) score += (h[64 + i] - x0[i]) * (h[64 + i] - x0[i]);
+      for (int i = 0; i < n; i++) score += (h[72 + i] - x0[i]) * (h[72 + i] - x0[i]);
       if (!have_best || score < best_score) {
         have_best = true; best_score = score;
-        memcpy(q_out, h + 64, n * 8);
-        *cost_out = h[100];
+        for (int i = 0; i < n; i++) q_out[i] = h[72 + i];
+        *cost_out = h[67];
       }
-      if (config->solution_mode == OPTIK_MODE_SPEED) break;  // the first wave with a success holds the lowest index
+      if (speed) break;  // the first wave with a success holds the lowest index
     }
   }
   return have_best ? 1 : 0;

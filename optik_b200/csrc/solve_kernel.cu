@@ -157,6 +157,18 @@ DEV void evaluate(const Joint& J, const se3& O, const double* s_tip, const doubl
 
 #include "ldl6.cuh"
 
+// ------------------------------------------------------------------ selection key (lib.rs:397-413)
+struct SelKey {
+  int has;  // 1 converged, 0 not, -1 nothing scanned
+  int evals;
+  double score;
+  unsigned long long restart;
+  unsigned long long idx;  // candidate index (job)
+};
+DEV bool sel_better(const SelKey& a, const SelKey& b) {  // a better than b
+  return (a.has > b.has) || (a.has == b.has && (a.score < b.score || (a.score == b.score && a.restart < b.restart)));
+}
+
 // ------------------------------------------------------------------ the solve kernel
 template <int TILE>
 __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(const __grid_constant__ SolveParams P) {
@@ -338,6 +350,65 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
     atomicAdd(P.counters + 1, (unsigned long long)n_evals);
     atomicAdd(P.counters + 2, (unsigned long long)n_conv);
   }
+
+  // ---------------- fused selection for single-target launches (Robot::ik): the LAST block to finish scans the candidate
+  // records, writes the packed record -- straight into mapped host memory when the host polls for it --, re-arms the
+  // persistent control words for the slot's next call and raises the completion flag.  One launch per ik() wave.
+  if (P.fused_record) {
+    __shared__ SelKey s_sel[128];
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(P.fused_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      SelKey me;
+      me.has = -1; me.evals = 0; me.score = 0.0; me.restart = ~0ull; me.idx = 0;
+      for (unsigned long long c = threadIdx.x; c < njobs; c += blockDim.x) {
+        const int st = ((volatile int*)P.cand_status)[c];
+        SelKey k;
+        k.has = (P.tol_f >= 0.0 && st == OPTIK_ST_STOPVAL) || (P.tol_df_user >= 0.0 && st == OPTIK_ST_FTOL) ||
+                (P.tol_dx >= 0.0 && st == OPTIK_ST_XTOL);
+        k.score = ((volatile double*)P.cand_score)[c];
+        k.restart = ((volatile unsigned long long*)P.cand_restart)[c];
+        k.idx = c; k.evals = 0;
+        if (me.has < 0 || sel_better(k, me)) me = k;
+      }
+      s_sel[threadIdx.x] = me;
+      __syncthreads();
+      for (int w = 64; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+          const SelKey o = s_sel[threadIdx.x + w];
+          if (o.has >= 0 && (s_sel[threadIdx.x].has < 0 || sel_better(o, s_sel[threadIdx.x]))) s_sel[threadIdx.x] = o;
+        }
+        __syncthreads();
+      }
+      const SelKey w = s_sel[0];
+      const int len = 8 + n;
+      if ((int)threadIdx.x < len) {
+        const int t = threadIdx.x;
+        double v = 0.0;
+        if (t == 0) v = w.has > 0 ? 1.0 : 0.0;
+        else if (t == 1) v = speed ? (double)w.restart : w.score;
+        else if (t == 2) v = (double)w.restart;
+        else if (t == 3) v = ((volatile double*)P.cand_f)[w.idx];
+        else if (t == 4) v = (double)((volatile int*)P.cand_status)[w.idx];
+        else if (t >= 8) v = ((volatile double*)P.cand_q)[w.idx * n + (t - 8)];
+        P.fused_record[t] = v;
+      }
+      if (P.fused_reset && threadIdx.x == 0) {  // persistent per-slot control words: ready for the next launch
+        *P.queue = 0ull;
+        *P.fused_done = 0u;
+        if (P.found) P.found[0] = ~0ull;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0 && P.fused_flag) *((volatile unsigned long long*)P.fused_flag) = P.fused_seq;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ selection across chunks (lib.rs:397-413)
@@ -345,16 +416,6 @@ __global__ void __launch_bounds__(128, OPTIK_SOLVE_MIN_BLOCKS) solve_kernel(cons
 // block reduces one slice of the candidates; with S > 1 (one target, tens of thousands of chunks) the slice winners go
 // to a partial array and a second launch (P.final_pass) reduces the S partials -- a single block walking 65 536
 // records serially costs more than the solve itself.
-struct SelKey {
-  int has;  // 1 converged, 0 not, -1 nothing scanned
-  int evals;
-  double score;
-  unsigned long long restart;
-  unsigned long long idx;  // candidate index (job)
-};
-DEV bool sel_better(const SelKey& a, const SelKey& b) {  // a better than b
-  return (a.has > b.has) || (a.has == b.has && (a.score < b.score || (a.score == b.score && a.restart < b.restart)));
-}
 __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ SelectParams P) {
   const unsigned long long t = blockIdx.x;
   const unsigned S = gridDim.y, slice = blockIdx.y;

@@ -91,6 +91,11 @@ struct SolveParams {
   double* fused_part_score;
   unsigned long long* fused_part_restart;
   unsigned* fused_done;
+  // tile kernel (single-target launches): completion flag the host polls (mapped host memory) and re-arming of the
+  // persistent control words (queue, fused_done, found[0]) by the last block
+  unsigned long long* fused_flag;
+  unsigned long long fused_seq;
+  int fused_reset;
   // optional: the last block also stores the record into every peer's exchange buffer (csrc/exchange_kernel.cu layout)
   const uint64_t* push_peers;         // device array of push_world base addresses, or null
   int push_rank, push_world;

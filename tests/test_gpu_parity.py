@@ -880,3 +880,33 @@ def test_peer_exchange_kernels_single_gpu():
     ob._check(lib.optik_gpu_exchange_select(r._h, bufs[0].data_ptr(), W, 20, out.data_ptr(), stream))
     torch.cuda.synchronize()
     assert out[0].item() == -1.0
+
+
+def test_ik_fresh_robot_default_config_and_concurrent_calls():
+    """(1) The first ik() on a freshly constructed Robot with the reference's DEFAULT config (Speed, max_time = 0.1 s, no
+    restart limit, config.rs:52-65) solves a reachable target: the max_time clock must not include the one-time device
+    initialisation.  (2) Robot::ik takes &self (lib.rs:241): eight host threads calling ik() on ONE Robot get the same
+    answers as serial calls (Speed mode is deterministic: lowest-index converged restart)."""
+    import threading
+    ch0 = O.Chain(ob.Robot.named("panda").chain())
+    rng = np.random.default_rng(77)
+    pairs = [(O.pose8_to_matrix(ch0.fk(rng.uniform(ch0.lb, ch0.ub))[1]).tolist(), rng.uniform(ch0.lb, ch0.ub)) for _ in range(64)]
+    fresh = ob.Robot.named("panda")
+    first = fresh.ik(ob.SolverConfig(), pairs[0][0], pairs[0][1])
+    assert first is not None and ch0.objective(np.array(first[0]), O.pose8_from_matrix(np.array(pairs[0][0]))) < 1e-6
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=64)
+    serial = [fresh.ik(cfg, m, x0) for m, x0 in pairs]
+    assert sum(s is not None for s in serial) >= 63
+    out = [None] * len(pairs)
+
+    def work(k):
+        for i in range(k, len(pairs), 8):
+            out[i] = fresh.ik(cfg, pairs[i][0], pairs[i][1])
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for a, b in zip(serial, out):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a[0] == b[0] and a[1] == b[1]
