@@ -550,27 +550,52 @@ def run_product(args):
         if s >= 3:
             sync_times.append(dt)
             sync_conv += c
-    # (b) pipelined.  One GPU: the C ABI's asynchronous host-buffer call.  Several GPUs: the same pass with the
-    # all-gather + global best-pick enqueued on the pass's stream (optik_b200.dist.HostStepPipeline), so no rank blocks
-    # on a collective between passes.
+    # (b) pipelined: the C ABI's asynchronous host-buffer call, E2E_DEPTH calls in flight.  Several GPUs: the same call
+    # also stores its candidate record into every peer (fused push), and the best-pick select + the D2H of the global
+    # best record are enqueued on the call's stream, so no rank blocks on the exchange between passes.
     if world > 1:
         dist.barrier()
     e2e_conv = 0
-    if world == 1:
+    D = E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI
+    if world == 1 or px is not None:
+        while len(sets) < D:
+            sets.append(((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
+                         ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)))
+        ext = [torch.cuda.ExternalStream(s_[2].handle, device=dev) for s_ in sets] if world > 1 else None
+        d_best = [torch.empty((obd.RECORD_HEAD + n,), dtype=torch.float64, device=dev) for _ in sets] if world > 1 else None
+        h_best = [torch.empty((obd.RECORD_HEAD + n,), dtype=torch.float64, pin_memory=True) for _ in sets] if world > 1 else None
+
+        def submit(s, k):
+            hrec, hrecord, stream = sets[k]
+            push = px.next_push() if world > 1 else None
+            robot.ik_attempts(cfg, tg_host[s], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
+                              record=hrecord, stream=stream, wait=False, push=push)
+            if world > 1:
+                with torch.cuda.stream(ext[k]):
+                    px.select(d_best[k], push[3])
+                    h_best[k].copy_(d_best[k], non_blocking=True)
+
+        def done(k):
+            sets[k][2].synchronize()
+            ok = 1 if world == 1 else int(h_best[k][0].item() >= 0)
+            return int((sets[k][0][2] == 1).sum()) * ok
+
+        for k in range(D):  # warm every slot
+            submit(0, k)
+        for k in range(D):
+            done(k)
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for s in range(Ke):
-            k = s % E2E_DEPTH_SINGLE
-            if s >= E2E_DEPTH_SINGLE:
-                e2e_conv += finish(k)
-            hrec, hrecord, stream = sets[k]
-            robot.ik_attempts(cfg, tg_host[s], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
-                              record=hrecord, stream=stream, wait=False)
-        for s in range(max(Ke - E2E_DEPTH_SINGLE, 0), Ke):
-            e2e_conv += finish(s % E2E_DEPTH_SINGLE)
+            k = s % D
+            if s >= D:
+                e2e_conv += done(k)
+            submit(s, k)
+        for s in range(max(Ke - D, 0), Ke):
+            e2e_conv += done(s % D)
     else:
-        # depth 4: the NCCL kernel of pass s only gets SM resources once pass s+1's solve kernel drains, so a pass
-        # completes about one pass late; four slots keep two solve kernels in flight regardless
-        D = E2E_DEPTH_MULTI
+        # NCCL fallback: optik_b200.dist.HostStepPipeline (torch copies + all-gather on a stream per slot), depth 4
         pipe = obd.HostStepPipeline(robot, cfg, R, rank=rank, world=world, tile=tile, depth=D, device=dev, exchange=px)
         for s in range(D):  # warm the slots (NCCL stream setup)
             pipe.submit(s, tg_host[0], x0_host)
@@ -692,6 +717,9 @@ def run_product(args):
                     "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
                             "OPTIK_BATCH_ASYNC (C ABI), one stream + buffer set per call in flight; host reads every pass's records"
                             if world == 1 else
+                            "the same asynchronous host-buffer call with the candidate record stored into every peer by the solve "
+                            "launch, then optik_gpu_exchange_select + D2H of the global best on the call's stream; %d passes in flight"
+                            % E2E_DEPTH_MULTI if px is not None else
                             "optik_b200.dist.HostStepPipeline: per pass H2D from pinned buffers -> optik_gpu_ik_attempts "
                             "(device path) -> NCCL all-gather of the candidate record -> optik_gpu_select_records -> D2H of "
                             "the records and the global best, all on the pass's stream; %d passes in flight" % E2E_DEPTH_MULTI),

@@ -562,6 +562,8 @@ class Robot:
             if record is None:
                 record = np.zeros(RECORD_HEAD + n)
             o.best_record_out = record.ctypes.data
+        if push is not None:
+            o.push_peers, o.push_rank, o.push_world, o.push_seq = int(push[0]), int(push[1]), int(push[2]), int(push[3])
         if counters is not None:
             o.counters = counters.ctypes.data
         _check(lib.optik_gpu_ik_attempts(self._h, C.byref(c), C.byref(o), target.ctypes.data, x0.ctypes.data,
