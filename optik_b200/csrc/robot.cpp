@@ -241,10 +241,8 @@ struct optik_robot {
     sm_count = prop.multiProcessorCount;
     const int tiles[3] = {8, 16, 32};
     for (int i = 0; i < 3; i++) CUDA_TRY(optik_solve_occupancy(tiles[i], &occ[i]));
-    if (n <= 8) {
-      CUDA_TRY(optik_solve_t1_occupancy(n, 1, &occ_t1[0]));
-      CUDA_TRY(optik_solve_t1_occupancy(n, 2, &occ_t1[1]));
-    }
+    for (int rows = 1; rows <= 2; rows++)  // 0 blocks/SM (or an error) = this chain's rows do not fit
+      if (optik_solve_t1_occupancy(n, rows, &occ_t1[rows - 1]) != 0) { occ_t1[rows - 1] = 0; cudaGetLastError(); }
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     // stream-ordered scratch comes from a pool this robot owns; its release threshold keeps blocks cached across
     // synchronisations (with the default of 0 every host-path call would turn into a fresh cudaMalloc)
@@ -261,7 +259,7 @@ struct optik_robot {
     seed_key_from_u64(RNG_SEED, key);
     if (key_dev.reserve(sizeof(key))) return fail(OPTIK_ERR_CUDA, "cudaMalloc(key) failed");
     CUDA_TRY(cudaMemcpy(key_dev.p, key, sizeof(key), cudaMemcpyHostToDevice));
-    if (n <= 8) {
+    if (occ_t1[0] > 0) {
       if (seed_cache.reserve((size_t)SEED_CACHE * n * sizeof(double))) return fail(OPTIK_ERR_CUDA, "cudaMalloc(seeds) failed");
       CUDA_TRY(optik_launch_seed_table((const double*)chain_dev.p, n, (const uint32_t*)key_dev.p, 0, SEED_CACHE,
                                        (double*)seed_cache.p, stream));
@@ -296,16 +294,19 @@ struct Plan {
 };
 // lanes per restart seed: 1 = thread-per-seed kernel (n <= 8), 8/16/32 = tile kernel.  `batch`: auto picks the
 // throughput layout (1) when it exists, otherwise / for single-target latency the smallest tile that fits.
-int choose_tile(int n, uint32_t want, bool batch) {
-  if (want == 1) return n <= 8 ? 1 : 0;
+int choose_tile(const optik_robot* r, uint32_t want, bool batch) {
+  const int n = r->n;
+  const bool t1_ok = r->occ_t1[0] > 0;  // the per-thread rows of this chain fit an SM's shared memory
+  if (want == 1) return t1_ok ? 1 : 0;
   if (want == 8 || want == 16 || want == 32) return (int)want >= n ? (int)want : 0;
   if (want != 0) return 0;
-  if (batch && n <= 8) return 1;
+  if (batch && t1_ok) return 1;
   return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 }
 // thread-per-seed kernel: rows = 2 keeps the trial columns in shared memory (2 blocks/SM), rows = 1 in local memory
 // (3 blocks/SM).  opts.variant forces one; the default is the measured better one.
 int t1_rows(const optik_robot* r, const optik_gpu_batch_opts* o, double attempts) {
+  if (r->occ_t1[1] <= 0) return 1;  // long chains: two column rows per thread do not fit
   if (o && (o->variant == 1 || o->variant == 2)) return (int)o->variant;
   // three blocks per SM win once every lane runs several attempts (throughput); with about one attempt per lane the
   // launch is a latency chain and two blocks per SM with the trial columns in shared memory are faster
@@ -378,8 +379,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
                  const double* d_targets, const double* d_x0, uint64_t T, uint64_t r_begin, uint64_t R, double* d_q,
                  double* d_f, int32_t* d_status, uint64_t* d_restart, int32_t* d_evals, uint64_t* d_counters,
                  unsigned long long max_ns, bool per_attempt_records, cudaStream_t s, double* d_best_record = nullptr) {
-  const int tile = choose_tile(r->n, o ? o->tile : 0, true);
-  if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (num_positions <= 8), 8, 16 or 32 and >= num_positions");
+  const int tile = choose_tile(r, o ? o->tile : 0, true);
+  if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (chains whose rows fit shared memory), 8, 16 or 32 and >= num_positions");
   const bool speed = cfg->solution_mode == OPTIK_MODE_SPEED;
   const int rows = t1_rows(r, o, per_attempt_records ? (double)R : (speed ? 2.0 * (double)T : (double)T * (double)(R < 4096 ? R : 4096)));
   SolveParams P{};
@@ -668,7 +669,6 @@ int optik_gpu_restart_seeds(const optik_robot* robot, uint64_t restart_begin, ui
     if (int rc = robot->ensure_gpu()) return rc;
   }
   CUDA_TRY(cudaSetDevice(robot->device));
-  if (robot->n > 8) return fail(OPTIK_ERR_UNSUPPORTED, "seed tables are built for num_positions <= 8");
   const int n = robot->n;
   if (memory == 1) {
     CUDA_TRY(optik_launch_seed_table((const double*)robot->chain_dev.p, n, (const uint32_t*)robot->key_dev.p, restart_begin,
@@ -981,7 +981,7 @@ static int ik_single(const optik_robot* robot, const optik_solver_config* config
   struct Release { IkSlot* s; ~Release() { s->busy.store(false, std::memory_order_release); } } release{sl};
   if (!sl->ready)
     if (int rc = ik_slot_init(robot, *sl)) return -rc;
-  const int tile = choose_tile(n, 0, false);  // single target: the low-latency tile layout, one restart per tile
+  const int tile = choose_tile(robot, 0, false);  // single target: the low-latency tile layout, one restart per tile
   const uint64_t max_restarts = config->max_restarts > 0 ? config->max_restarts : ~0ull;  // lib.rs:273-277
   const bool speed = config->solution_mode == OPTIK_MODE_SPEED;
   SolveParams P{};

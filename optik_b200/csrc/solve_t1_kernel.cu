@@ -1,4 +1,5 @@
-// solve_t1_kernel.cu -- the restart solve with ONE THREAD PER RESTART SEED (throughput layout, n <= 8).
+// solve_t1_kernel.cu -- the restart solve with ONE THREAD PER RESTART SEED (throughput layout; any chain whose
+// per-thread rows fit the SM's shared memory: n <= 27 with 128-thread blocks).
 //
 // Same path, objective, stop rules, seeds and LM step as solve_kernel.cu (reference: crates/optik/src/lib.rs:297-413,
 // objective.rs:40-110, kinematics.rs:123-196, math.rs:40-203), but the evaluation order is sequential per seed:
@@ -42,12 +43,12 @@ constexpr unsigned DYN_NONE = 0xffffffffu;
 
 DEV int t1_row_units(int n) { return (3 * n) | 1; }  // 16-byte units per column row, forced odd
 
-// One ChaCha8 block -> the first 8 u64 of stream `stream` (enough for n <= 8 joints).  Rolled and not inlined: it is the
+// ChaCha8 block `counter` of stream `stream` -> 8 u64 (joint j draws u64 number j: block j / 8, word pair j % 8).  Rolled and not inlined: it is the
 // cold path of the solve kernel (restart indices beyond the seed table) and the whole of seed_table_kernel.
-__device__ __noinline__ void chacha8_block(const uint32_t* key, uint64_t stream, uint64_t* out8) {
+__device__ __noinline__ void chacha8_block(const uint32_t* key, uint64_t counter, uint64_t stream, uint64_t* out8) {
   uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
                     key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
-                    0u, 0u, (uint32_t)stream, (uint32_t)(stream >> 32)};
+                    (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
   uint32_t x[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) x[i] = s[i];
@@ -75,14 +76,16 @@ __global__ void __launch_bounds__(128) seed_table_kernel(const double* __restric
   uint32_t key[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) key[k] = key_g[k];
-  uint64_t u[8];
-  chacha8_block(key, r, u);
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    uint64_t u[8];
+    chacha8_block(key, (uint64_t)(j0 >> 3), r, u);
 #pragma unroll
-  for (int j = 0; j < 8; j++)
-    if (j < n) {
-      const double* jc = chain + OPTIK_CHAIN_STRIDE * j;
-      out[i * n + j] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
-    }
+    for (int j = 0; j < 8; j++)
+      if (j0 + j < n) {
+        const double* jc = chain + OPTIK_CHAIN_STRIDE * (j0 + j);
+        out[i * n + j0 + j] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
+      }
+  }
 }
 
 // Known-answer hook: the raw 16-word ChaCha8 block (counter 0) of `stream` under `key`, as the kernels compute it
@@ -90,9 +93,8 @@ __global__ void chacha8_kat_kernel(const uint32_t* __restrict__ key_g, unsigned 
   uint32_t key[8];
   for (int k = 0; k < 8; k++) key[k] = key_g[k];
   uint64_t u[8];
-  chacha8_block(key, stream, u);
+  chacha8_block(key, 0, stream, u);
   for (int k = 0; k < 8; k++) { out16[2 * k] = (uint32_t)u[k]; out16[2 * k + 1] = (uint32_t)(u[k] >> 32); }
-  // words 8..15 of the block are not consumed by the solver (n <= 8 joints use 8 u64 = 16 words: all of them)
 }
 
 // ---- help-ticket ring of the dynamic scheduler: head = dyn_ctl[0], tail = dyn_ctl[16] (separate 128-byte lines).
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   double* qt_ = s_qt + tid;
   double2* const row0 = s_rows + (size_t)tid * units;  // rows[k] = row0 + k * row_stride
   const size_t row_stride = (size_t)T1_THREADS * units;
-  double2 ltrial[ROWS == 1 ? 3 * 8 : 1];  // ROWS == 1: the trial point's body columns (thread-local memory)
+  double2 ltrial[ROWS == 1 ? 3 * OPTIK_MAX_DOF : 1];  // ROWS == 1: the trial point's body columns (thread-local memory)
   const int sched = P.sched;
   const unsigned long long njobs = sched == 1 ? P.T : P.T * (unsigned long long)P.C;
   const bool speed = (P.mode == 2);
@@ -331,32 +333,38 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         }
       }
       if (got) {  // restart 0 = the caller's seed, i >= 1 = ChaCha8 stream i (lib.rs:360-370)
-        if (r_idx == 0) {  // (loads issued together: one memory latency, not n)
-          double sv[8];
+        if (r_idx == 0) {  // (loads issued eight at a time: one memory latency per group, not per joint)
+          for (int j0 = 0; j0 < n; j0 += 8) {
+            double sv[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) if (j < n) sv[j] = P.x0[tgt_id * n + j];
+            for (int j = 0; j < 8; j++) if (j0 + j < n) sv[j] = P.x0[tgt_id * n + j0 + j];
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            if (j < n) {
-              const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-              qt_[j * T1_THREADS] = fmin(fmax(sv[j], jc[12]), jc[13]);
-            }
+            for (int j = 0; j < 8; j++)
+              if (j0 + j < n) {
+                const double* jc = s_chain + OPTIK_CHAIN_STRIDE * (j0 + j);
+                qt_[(j0 + j) * T1_THREADS] = fmin(fmax(sv[j], jc[12]), jc[13]);
+              }
+          }
         } else if (r_idx - P.seed_begin < P.seed_count) {
           const double* sd = P.seed_tab + (r_idx - P.seed_begin) * n;
-          double sv[8];
+          for (int j0 = 0; j0 < n; j0 += 8) {
+            double sv[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) if (j < n) sv[j] = __ldg(sd + j);
+            for (int j = 0; j < 8; j++) if (j0 + j < n) sv[j] = __ldg(sd + j0 + j);
 #pragma unroll
-          for (int j = 0; j < 8; j++) if (j < n) qt_[j * T1_THREADS] = sv[j];
+            for (int j = 0; j < 8; j++) if (j0 + j < n) qt_[(j0 + j) * T1_THREADS] = sv[j];
+          }
         } else {
-          uint64_t u[8];
-          chacha8_block(P.key, r_idx, u);
+          for (int j0 = 0; j0 < n; j0 += 8) {
+            uint64_t u[8];
+            chacha8_block(P.key, (uint64_t)(j0 >> 3), r_idx, u);
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            if (j < n) {
-              const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-              qt_[j * T1_THREADS] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
-            }
+            for (int j = 0; j < 8; j++)
+              if (j0 + j < n) {
+                const double* jc = s_chain + OPTIK_CHAIN_STRIDE * (j0 + j);
+                qt_[(j0 + j) * T1_THREADS] = fmin(fmax(uniform_f64(u[j], jc[14], jc[15]), jc[12]), jc[13]);
+              }
+          }
         }
         have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
         running = true;

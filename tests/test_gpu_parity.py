@@ -21,8 +21,9 @@ def robot_and_chain(name):
 
 
 def twin_layout(ch, tile=0):
-    """Which twin mirrors the kernel the library picks: thread-per-seed (1) for tile=1 or auto with n <= 8."""
-    return 1 if (tile == 1 or (tile == 0 and ch.n <= 8)) else 0
+    """Which twin mirrors the kernel the library picks: thread-per-seed (1) for tile=1 or auto in batched calls (every
+    chain whose per-thread rows fit shared memory: n <= 27), else the tile kernel's lane-per-joint order (0)."""
+    return 1 if (tile == 1 or (tile == 0 and ch.n <= 27)) else 0
 
 
 def targets_for(ch, rng, T):
@@ -320,23 +321,25 @@ def test_config3_full_size_properties():
 
 
 def test_config4_full_size_properties():
-    """20-DOF snake, 262 144 seeds to one target (BASELINE config 4, tile kernel): converged records re-evaluate below
-    tol_f inside the (tight) limits; a sample of seeds is bit-identical to the twin; pinned joints sit ON a limit."""
+    """20-DOF snake, 262 144 seeds to one target (BASELINE config 4): converged records re-evaluate below tol_f inside
+    the (tight) limits; a sample of seeds is bit-identical to the twin; pinned joints sit ON a limit.  Runs the default
+    layout (thread-per-seed kernel, one column row per thread) and the tile kernel (one warp per seed)."""
     r, ch = robot_and_chain("snake20")
     rng = np.random.default_rng(42)
     tgt = ch.fk(rng.uniform(ch.lb, ch.ub))[1]
     x0 = 0.5 * (ch.lb + ch.ub)
     R = 262144
     cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
-    q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R)
-    ok = st == 1
-    assert ok.mean() > 0.8
-    fe = r.eval_batch(q, tgt, want=("f",))["f"]
-    assert np.all(fe[ok] < cfg.tol_f) and np.all(q >= ch.lb) and np.all(q <= ch.ub)
-    assert ((q[ok] == ch.lb) | (q[ok] == ch.ub)).any()  # the joint-limit stress really exercises the projection
-    for i in rng.choice(R, 64, replace=False):
-        tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1, O.twin_params(layout=0))
-        assert tst[0] == st[i] and tev[0] == ev[i] and np.array_equal(tq[0], q[i])
+    for tile in (0, 32):
+        q, f, st, ev = r.ik_attempts(cfg, tgt, x0, R if tile == 0 else R // 8, tile=tile)
+        ok = st == 1
+        assert ok.mean() > 0.8
+        fe = r.eval_batch(q, tgt, want=("f",))["f"]
+        assert np.all(fe[ok] < cfg.tol_f) and np.all(q >= ch.lb) and np.all(q <= ch.ub)
+        assert ((q[ok] == ch.lb) | (q[ok] == ch.ub)).any()  # the joint-limit stress really exercises the projection
+        for i in rng.choice(len(st), 64, replace=False):
+            tq, tf, tst, tev = O.twin_attempts(ch, tgt, x0, int(i), int(i) + 1, O.twin_params(layout=twin_layout(ch, tile)))
+            assert tst[0] == st[i] and tev[0] == ev[i] and np.array_equal(tq[0], q[i])
 
 
 def test_config5_shard_full_size_properties():
@@ -438,11 +441,13 @@ def arm(n, prismatic_at=(), tip=("0 0.05 0.1", "0.3 0 0.2")):
 @pytest.mark.parametrize("n,pris,tip,tiles", [
     (8, (), ("0 0.05 0.1", "0.3 0 0.2"), (1, 8, 16)),      # n == tile width: the tip cannot ride the scan (8 lanes)
     (8, (), None, (1, 8)),                                   # no tip joint at all
-    (16, (), ("0 0 0.1", "0 0 0"), (16, 32)),                # n == 16
+    (16, (), ("0 0 0.1", "0 0 0"), (1, 16, 32)),             # n == 16
     (5, (2,), ("0.1 0 0", "0 0.5 0"), (1, 8)),               # prismatic joint mid-chain (reference FK supports it)
     (4, (0, 3), None, (1, 8, 32)),                           # prismatic first and last
     (1, (), ("0 0 0.2", "0 0 0"), (1, 8)),                   # single joint
-    (12, (5,), ("0 0 0.1", "0.1 0 0"), (16, 32)),            # tile kernel only (n > 8), with a prismatic joint
+    (12, (5,), ("0 0 0.1", "0.1 0 0"), (1, 16, 32)),         # n > 8 (seeds span two ChaCha8 blocks), a prismatic joint
+    (27, (), ("0 0 0.05", "0 0 0"), (1, 32)),                # the longest chain whose rows fit the thread-per-seed kernel
+    (30, (), ("0 0 0.05", "0 0 0"), (0, 32)),                # beyond it: the tile kernel (auto)
 ])
 def test_chain_shapes_match_twin_and_oracle(n, pris, tip, tiles):
     urdf, base, ee = arm(n, pris, tip)
