@@ -28,8 +28,6 @@ namespace optik {
 
 DEV uint32_t e_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr int EVAL_THREADS = 128;
-constexpr int EVAL_WARPS = EVAL_THREADS / 32;
 
 DEV se3 e_load_pose8(const double* p) {
   se3 r;
@@ -65,30 +63,32 @@ DEV void e_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
 
 // N = compile-time joint count (fully unrolled joint loops: static shared-memory offsets, the scheduler overlaps one
 // joint's sin/cos with the previous joint's quaternion chain); N = 0 reads n from the parameters.
+// TB = threads per block: 128, or 64 for long chains (n > 12) whose 48n-byte rows would leave one 128-thread block per SM
+// (n = 20: 4 warps/SM with 128 threads, 6 with 64).
 // COLS = Jacobian columns are needed (jac_out or grad_out): per-thread rows in shared memory, ONE tile buffer per warp
 // (refilled while the warp forms objective / gradient / stores).  COLS = false is the FK-only launch: no rows, TWO
 // tile buffers per warp, the next tile is requested before the current one is consumed.
-template <int N, bool COLS>
-__global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_constant__ EvalParams P) {
+template <int N, bool COLS, int TB>
+__global__ void __launch_bounds__(TB, TB == 128 ? 4 : 6) eval_kernel(const __grid_constant__ EvalParams P) {
   extern __shared__ __align__(128) double smem[];
   // layout: chain blob | block mbarrier (16 B) | two mbarriers per warp (8 B each) | per-thread Jacobian rows (COLS) |
-  //         per-warp joint-vector tiles [EVAL_WARPS][NBUF][32 * n] | per-joint constants origin_q (x) axis [n][4]
+  //         per-warp joint-vector tiles [(TB / 32)][NBUF][32 * n] | per-joint constants origin_q (x) axis [n][4]
   constexpr int NBUF = COLS ? 1 : 2;
   double* s_chain = smem;
   const int n = N ? N : P.n;
   const int chain_doubles = OPTIK_CHAIN_STRIDE * n + 8;
   uint64_t* s_bar = (uint64_t*)(smem + chain_doubles);
   uint64_t* s_wbar = (uint64_t*)(smem + chain_doubles + 2);
-  double2* s_rows = (double2*)(smem + chain_doubles + 2 + 2 * EVAL_WARPS);
+  double2* s_rows = (double2*)(smem + chain_doubles + 2 + 2 * (TB / 32));
   const int units = eval_row_units(n);
-  double* s_q = (double*)(s_rows + (COLS ? (size_t)EVAL_THREADS * units : 0));
-  double2* s_oa = (double2*)(s_q + (size_t)EVAL_WARPS * NBUF * 32 * n);  // [n][2]
+  double* s_q = (double*)(s_rows + (COLS ? (size_t)TB * units : 0));
+  double2* s_oa = (double2*)(s_q + (size_t)(TB / 32) * NBUF * 32 * n);  // [n][2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_bar)));
 #pragma unroll
-    for (int w = 0; w < 2 * EVAL_WARPS; w++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_wbar + w)));
+    for (int w = 0; w < 2 * (TB / 32); w++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(e_smem_u32(s_wbar + w)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
   const uint32_t wbar0 = e_smem_u32(s_wbar + 2 * warp);
   const uint32_t tile_bytes = 256u * (uint32_t)n;
   const bool q_aligned = (((unsigned long long)P.q) & 15ull) == 0ull;
-  const unsigned long long stride = (unsigned long long)gridDim.x * EVAL_THREADS;
-  unsigned long long base = (unsigned long long)blockIdx.x * EVAL_THREADS + 32ull * warp;  // first configuration of my tile
+  const unsigned long long stride = (unsigned long long)gridDim.x * TB;
+  unsigned long long base = (unsigned long long)blockIdx.x * TB + 32ull * warp;  // first configuration of my tile
   uint32_t parity = 0, pending = 0;  // bit b: phase parity of barrier b / a bulk load into buffer b is in flight
   auto fetch_tile = [&](unsigned long long b, int buf) {
     double* qb = qb0 + buf * 32 * n;
@@ -285,17 +285,22 @@ __global__ void __launch_bounds__(EVAL_THREADS, 4) eval_kernel(const __grid_cons
 
 }  // namespace optik
 
+static int eval_threads(int n) { return n > 12 ? 64 : 128; }
 static const void* eval_entry(int n, bool cols) {
   switch (n) {
-    case 6: return cols ? (const void*)optik::eval_kernel<6, true> : (const void*)optik::eval_kernel<6, false>;
-    case 7: return cols ? (const void*)optik::eval_kernel<7, true> : (const void*)optik::eval_kernel<7, false>;
-    default: return cols ? (const void*)optik::eval_kernel<0, true> : (const void*)optik::eval_kernel<0, false>;
+    case 6: return cols ? (const void*)optik::eval_kernel<6, true, 128> : (const void*)optik::eval_kernel<6, false, 128>;
+    case 7: return cols ? (const void*)optik::eval_kernel<7, true, 128> : (const void*)optik::eval_kernel<7, false, 128>;
+    default:
+      if (eval_threads(n) == 64) return cols ? (const void*)optik::eval_kernel<0, true, 64> : (const void*)optik::eval_kernel<0, false, 64>;
+      return cols ? (const void*)optik::eval_kernel<0, true, 128> : (const void*)optik::eval_kernel<0, false, 128>;
   }
 }
+extern "C" int optik_eval_threads(int n) { return eval_threads(n); }
 extern "C" int optik_eval_smem_bytes(int n, int cols) {
-  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2 + 2 * optik::EVAL_WARPS) +
-               (cols ? 16ull * optik::EVAL_THREADS * (size_t)((3 * n) | 1) : 0ull) +
-               sizeof(double) * 32ull * n * optik::EVAL_WARPS * (cols ? 1 : 2) + sizeof(double) * 4ull * n);
+  const size_t tb = (size_t)eval_threads(n), warps = tb / 32;
+  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 2 + 2 * warps) +
+               (cols ? 16ull * tb * (size_t)((3 * n) | 1) : 0ull) +
+               sizeof(double) * 32ull * n * warps * (cols ? 1 : 2) + sizeof(double) * 4ull * n);
 }
 static bool eval_wants_cols(const EvalParams* p) { return p->jac_out != nullptr || p->grad_out != nullptr; }
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream) {
@@ -305,7 +310,7 @@ extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream) 
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   void* args[] = {(void*)p};
-  e = cudaLaunchKernel(fn, dim3(blocks), dim3(optik::EVAL_THREADS), args, smem, (cudaStream_t)stream);
+  e = cudaLaunchKernel(fn, dim3(blocks), dim3(eval_threads(p->n)), args, smem, (cudaStream_t)stream);
   return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 // resident blocks per SM: the kernel is persistent (grid-stride over tiles), so the launcher sizes the grid to
@@ -315,5 +320,5 @@ extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm) {
   const void* fn = eval_entry(n, cols != 0);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, optik::EVAL_THREADS, smem);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, eval_threads(n), smem);
 }

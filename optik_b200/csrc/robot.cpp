@@ -31,6 +31,7 @@ extern "C" int optik_select_partial_bytes(void);
 extern "C" int optik_solve_occupancy(int tile, int* blocks_per_sm);
 extern "C" int optik_launch_eval(const EvalParams* p, int blocks, void* stream);
 extern "C" int optik_eval_smem_bytes(int n, int cols);
+extern "C" int optik_eval_threads(int n);
 extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stream);
 extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows, int blocks, void* stream);
@@ -785,7 +786,8 @@ int optik_gpu_eval_batch(const optik_robot* robot, const double* q, const double
     occ_cache[cols][n].store(per_sm, std::memory_order_relaxed);
   }
   if (per_sm < 1) return fail(OPTIK_ERR_UNSUPPORTED, "evaluator tile does not fit one SM");
-  const uint64_t nblk = (B + 127) / 128, resident = (uint64_t)robot->sm_count * (uint64_t)per_sm;
+  const uint64_t tb = (uint64_t)optik_eval_threads(n);
+  const uint64_t nblk = (B + tb - 1) / tb, resident = (uint64_t)robot->sm_count * (uint64_t)per_sm;
   const int blocks = (int)(nblk < resident ? nblk : resident);
   if (memory == 1) {
     P.q = q; P.targets = targets; P.ee_out = ee_out; P.jac_out = jac_out; P.f_out = f_out; P.grad_out = grad_out;
