@@ -875,7 +875,8 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
     if (rc) return rc;
     // the reference panics on a seed outside the limits (lib.rs:251-254); device seeds cannot be checked without a
     // sync, so they are clamped and the target's status carries OPTIK_STATUS_FLAG_SEED_CLAMPED
-    if (r_begin == 0)
+    // (per-attempt launches of the thread-per-seed kernel set the flag on restart 0's record themselves)
+    if (r_begin == 0 && !(per_attempt && T == 1 && choose_tile(robot, opts ? opts->tile : 0, true) == 1))
       CUDA_TRY(optik_launch_flag_clamped((const double*)robot->chain_dev.p, n, x0, T, status_out, 1, s));
     return OPTIK_OK;
   }
@@ -908,7 +909,7 @@ static int batch_common(const optik_robot* robot, const optik_solver_config* con
                             evals_host ? (int32_t*)(d + o_e) : nullptr, want_cnt ? (uint64_t*)(d + o_c) : nullptr, max_ns,
                             per_attempt, s, want_best ? (double*)(d + o_br) : nullptr))
     return rc;
-  if (async && r_begin == 0)
+  if (async && r_begin == 0 && !(per_attempt && T == 1 && choose_tile(robot, opts ? opts->tile : 0, true) == 1))
     CUDA_TRY(optik_launch_flag_clamped((const double*)robot->chain_dev.p, n, (const double*)(d + o_x), T, (int*)(d + o_s), 1, s));
   CUDA_TRY(cudaMemcpyAsync(q_out, d + o_q, NO * n * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(cost_out, d + o_f, NO * 8, cudaMemcpyDeviceToHost, s));

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
   // ---- per-thread state.  sched 0: a "job" is one (target, chunk); sched 1: a "chain" on one target; sched 2: one attempt
   unsigned long long job = 0, tgt_id = 0, r_idx = 0, r_next = 0;
   bool running = false, job_open = false, best_has = false, rec_any = false, done = false;
+  bool seed_clamped = false;  // this attempt started from a caller seed that had to be clamped into the limits
   bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
   unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
@@ -342,7 +343,9 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
             for (int j = 0; j < 8; j++)
               if (j0 + j < n) {
                 const double* jc = s_chain + OPTIK_CHAIN_STRIDE * (j0 + j);
-                qt_[(j0 + j) * T1_THREADS] = fmin(fmax(sv[j], jc[12]), jc[13]);
+                const double cl = fmin(fmax(sv[j], jc[12]), jc[13]);
+                seed_clamped |= !(cl == sv[j]);  // the reference panics here (lib.rs:251-254); see OPTIK_STATUS_FLAG_SEED_CLAMPED
+                qt_[(j0 + j) * T1_THREADS] = cl;
               }
           }
         } else if (r_idx - P.seed_begin < P.seed_count) {
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
               }
           }
         }
+        if (r_idx != 0) seed_clamped = false;
         have_cur = 0; slow = 0; evals = 0; lambda = P.lambda0;
         running = true;
       }
@@ -481,7 +485,9 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           rec_any = true;
 #pragma unroll 1
           for (int j = 0; j < n; j++) P.cand_q[job * n + j] = qt_[j * T1_THREADS];
-          P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx; P.cand_status[job] = status;
+          P.cand_f[job] = ft; P.cand_score[job] = score; P.cand_restart[job] = r_idx;
+          // per-attempt records: the caller's seed (restart 0) carries the clamped-seed flag itself (no extra launch)
+          P.cand_status[job] = (sched == 2 && seed_clamped) ? (status | 0x100) : status;
           if (sched == 2) P.cand_evals[job] = evals;
         }
         if (sched == 2 && P.fused_record) {  // this lane's best attempt so far, for the in-kernel selection pass
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
         else if (tid == 1) v = speed ? (double)rs : ((volatile double*)P.cand_score)[win];
         else if (tid == 2) v = (double)rs;
         else if (tid == 3) v = ((volatile double*)P.cand_f)[win];
-        else if (tid == 4) v = (double)((volatile int*)P.cand_status)[win];
+        else if (tid == 4) v = (double)(((volatile int*)P.cand_status)[win] & 0xff);
         else if (tid >= 8 && tid < len) v = ((volatile double*)P.cand_q)[win * n + (tid - 8)];
         if (tid < len) P.fused_record[tid] = v;
         if (P.push_peers) {  // cross-GPU: row `push_rank` of slot push_seq % 8 in every peer's buffer, then its flag

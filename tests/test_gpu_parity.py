@@ -915,3 +915,34 @@ def test_ik_fresh_robot_default_config_and_concurrent_calls():
         assert (a is None) == (b is None)
         if a is not None:
             assert a[0] == b[0] and a[1] == b[1]
+
+
+def test_device_path_flags_clamped_seeds():
+    """The reference panics on a seed outside the joint limits (lib.rs:251-254); host-memory calls reject it, device-memory
+    calls cannot look without a sync: the kernels clamp the seed and the status word carries
+    OPTIK_STATUS_FLAG_SEED_CLAMPED (the success classification ignores the flag)."""
+    import torch
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(9)
+    T = 5000
+    tg = torch.from_numpy(targets_for(ch, rng, 64)).cuda().repeat(T // 64 + 1, 1)[:T].contiguous()
+    x0 = torch.from_numpy(rng.uniform(ch.lb, ch.ub, size=(T, ch.n))).cuda()
+    bad = [3, 77, 4999]
+    for t in bad:
+        x0[t, t % ch.n] = ch.ub[t % ch.n] + 0.5
+    cfg = ob.SolverConfig(max_time=0.0, max_restarts=16)
+    for kw in ({}, {"static": True}, {"tile": 8}):
+        q, f, st = r.ik_batch(cfg, tg, x0, restarts=16, **kw)
+        st = st.cpu().numpy()
+        flagged = np.where(st & ob.STATUS_FLAG_SEED_CLAMPED)[0]
+        assert list(flagged) == bad, (kw, flagged)
+        assert cfg.is_success(st).mean() > 0.99 and np.all((st & ob.STATUS_CODE_MASK) <= 7)
+    # per-attempt records: the flag sits on restart 0's record only
+    qcfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=64)
+    for tile in (0, 8):
+        qa, fa, sa, ea, rec = r.ik_attempts(qcfg, tg[3], x0[3], 64, tile=tile, best=True)
+        sa = sa.cpu().numpy()
+        assert sa[0] & ob.STATUS_FLAG_SEED_CLAMPED and not np.any(sa[1:] & ob.STATUS_FLAG_SEED_CLAMPED)
+        assert float(rec[4]) == float(int(rec[4]) & ob.STATUS_CODE_MASK)
+        qb, fb, sb, eb = r.ik_attempts(qcfg, tg[5], x0[5], 64, tile=tile)
+        assert not np.any(sb.cpu().numpy() & ob.STATUS_FLAG_SEED_CLAMPED)
