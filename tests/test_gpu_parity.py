@@ -946,3 +946,37 @@ def test_device_path_flags_clamped_seeds():
         assert float(rec[4]) == float(int(rec[4]) & ob.STATUS_CODE_MASK)
         qb, fb, sb, eb = r.ik_attempts(qcfg, tg[5], x0[5], 64, tile=tile)
         assert not np.any(sb.cpu().numpy() & ob.STATUS_FLAG_SEED_CLAMPED)
+
+
+@pytest.mark.parametrize("T", [600, 9000])
+def test_batch_default_budget_runs_until_max_time(T):
+    """The reference's default budget -- no restart limit, max_time bounds the call (config.rs:52-65, lib.rs:260-277) --
+    on the batched path: reachable targets are solved, unreachable ones keep drawing restarts until the deadline
+    (tests/test_ik.rs:24-43 at batch size), through the static (small T) and the dynamic (large T) schedule."""
+    import time
+    r, ch = robot_and_chain("ur3e")
+    rng = np.random.default_rng(21)
+    tg = targets_for(ch, rng, 200)
+    tg = np.tile(tg, (T // 200, 1))
+    far = np.arange(0, T, 50)
+    tg[far, 4:7] = [100.0, 100.0, 100.0]  # unreachable translations
+    x0 = rng.uniform(ch.lb, ch.ub, size=(T, ch.n))
+    cfg = ob.SolverConfig(max_time=0.05)  # Speed, max_restarts = u64::MAX
+    r.ik_batch(ob.SolverConfig(max_time=0.0, max_restarts=2), tg[:8], x0[:8])  # warm the context
+    t0 = time.perf_counter()
+    q, f, st = r.ik_batch(cfg, tg, x0)
+    dt = time.perf_counter() - t0
+    ok = cfg.is_success(st)
+    assert not ok[far].any() and 0.04 <= dt <= 0.25, dt
+    near = np.setdiff1d(np.arange(T), far)
+    assert ok[near].mean() > 0.999
+    for t in near[:: max(1, len(near) // 64)]:
+        assert ch.objective(q[t], tg[t]) < cfg.tol_f
+    with pytest.raises(ob.OptikError, match="forever"):
+        r.ik_batch(ob.SolverConfig(max_time=0.0, max_restarts=0) if False else _no_budget(), tg[:4], x0[:4])
+
+
+def _no_budget():
+    c = ob.SolverConfig(max_time=0.1)
+    c.max_time = 0.0  # bypass the constructor's check (crates/optik-py/src/lib.rs:45-47): the C ABI refuses it too
+    return c
