@@ -612,9 +612,14 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     for (int j = 0; j < n; j++) {
       const double2 a0 = crow[3 * j + 0], a1 = crow[3 * j + 1], a2 = crow[3 * j + 2];
       const double m = ((free_mask >> j) & 1u) ? 1.0 : 0.0;
-      const double Jm[6] = {m * a0.x, m * a0.y, m * a1.x, m * a1.y, m * a2.x, m * a2.y};
+      const double c[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
       const double* jc = s_chain + OPTIK_CHAIN_STRIDE * j;
-      qt_[j * T1_THREADS] = fmin(fmax(qc[j * T1_THREADS] - dot6(Jm, y), jc[12]), jc[13]);
+      // pinned joints stay put (m = 0); the projection on [lb, ub] as two compares (fmin / fmax carry NaN-quieting
+      // code this loop does not need: a NaN step stays NaN and ends the attempt as OPTIK_ST_NAN at the next evaluation)
+      double x = qc[j * T1_THREADS] - m * dot6(c, y);
+      x = x < jc[12] ? jc[12] : x;
+      x = x > jc[13] ? jc[13] : x;
+      qt_[j * T1_THREADS] = x;
     }
   }
 

@@ -481,9 +481,10 @@ static int twin_attempt_t1(const twin_chain* c, const twin_params* P, se3t tgt, 
     for (int a = 0; a < 6; a++) A[a][a] = A[a][a] + lambda;
     ldl6_solve(A, rc, y);
     for (int j = 0; j < n; j++) {
-      double Jm[6];
-      for (int a = 0; a < 6; a++) Jm[a] = m[j] * C[j][a];
-      qt_[j] = fmin(fmax(qc[j] - dot6(Jm, y), c->lb[j]), c->ub[j]);
+      double x = qc[j] - m[j] * dot6(C[j], y);
+      x = x < c->lb[j] ? c->lb[j] : x;
+      x = x > c->ub[j] ? c->ub[j] : x;
+      qt_[j] = x;
     }
   }
   memcpy(q_out, qt_, sizeof(double) * n);
