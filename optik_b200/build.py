@@ -21,17 +21,19 @@ def sources():
     return deps
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(force=False, verbose=False, defines=(), out=OUT):
+    """`defines` / `out`: experiment builds (tools/exp_variants.py) of the same sources under other -D switches."""
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in sources()):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-           "-shared", "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-o", OUT]
+           "-shared", "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-o", out]
+    cmd += ["-D" + d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SRCS]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

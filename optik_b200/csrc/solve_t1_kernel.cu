@@ -41,6 +41,9 @@ constexpr int T1_THREADS = 128;
 constexpr unsigned FULLMASK = 0xffffffffu;
 constexpr unsigned DYN_NONE = 0xffffffffu;
 
+// hot joint loops: fully unrolled when the joint count is a template constant (NS), rolled otherwise
+#define T1_HOT_UNROLL _Pragma("unroll (NS ? NS : 1)")
+
 DEV int t1_row_units(int n) { return (3 * n) | 1; }  // 16-byte units per column row, forced odd
 
 // ChaCha8 block `counter` of stream `stream` -> 8 u64 (joint j draws u64 number j: block j / 8, word pair j % 8).  Rolled and not inlined: it is the
@@ -140,10 +143,10 @@ DEV void warp_prefetch(const void* p, unsigned long long bytes, int lane) {
   }
 }
 
-template <bool GENERAL, int ROWS>
+template <bool GENERAL, int ROWS, int NS>
 __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) double smem[];
-  const int n = P.n;
+  const int n = NS ? NS : P.n;  // NS: the joint count as a compile-time constant (joint loops fully unrolled), 0 = any
   // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[ROWS][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
   //         per-joint constants origin_q (x) (axis, 0) [n][4]
   double* s_chain = smem;
@@ -381,7 +384,11 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     double2* trow = (ROWS == 1) ? ltrial : row0 + (size_t)(cur ^ 1) * row_stride;  // trial body columns
     se3 Ci = load_pose8(s_tip);  // C_n = tip^-1
     const se3 tgt = load_pose8(P.targets + 8 * tgt_id);  // issued here: the recursion hides its latency
-#pragma unroll 1
+    // unrolled instances: sin/cos of joint j - 1 is computed during joint j's quaternion chain (independent work under
+    // a dependent chain; measured slower in the rolled loop)
+    double s_nx = 0.0, c_nx = 0.0;
+    if (NS) dsincos(0.5 * qt_[(n - 1) * T1_THREADS], s_nx, c_nx);
+T1_HOT_UNROLL
     for (int j = n - 1; j >= 0; j--) {
       const double2* jc = (const double2*)(s_chain + OPTIK_CHAIN_STRIDE * j);
       const double2 c0 = jc[0], c1 = jc[1], c2 = jc[2], c3 = jc[3], c4 = jc[4], c5 = jc[5];
@@ -399,7 +406,10 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       v3 lt = mk3(c0.x, c0.y, c1.x);
       if (!pris) {
         double s, c;
-        dsincos(0.5 * qj, s, c);
+        if (NS) {
+          s = s_nx; c = c_nx;
+          if (j > 0) dsincos(0.5 * qt_[(j - 1) * T1_THREADS], s_nx, c_nx);
+        } else dsincos(0.5 * qj, s, c);
         lq.x = -fma(c, c2.x, s * a0.x); lq.y = -fma(c, c2.y, s * a0.y); lq.z = -fma(c, c3.x, s * a1.x);
         lq.w = fma(c, c3.y, s * a1.y);
       } else {
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     }
 
     if (accept) {  // current point <- trial point; body columns -> task columns
-#pragma unroll 1
+T1_HOT_UNROLL
       for (int j = 0; j < n; j++) qc[j * T1_THREADS] = qt_[j * T1_THREADS];
       fc = ft; have_cur = 1;
 #pragma unroll
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
       task_mats(ec, Jm, CJ);
       double2* wrow = (ROWS == 1) ? row0 : trow;  // ROWS == 2: converted in place, then the rows swap
       double2 n0 = trow[0], n1 = trow[1], n2 = trow[2];  // software-pipelined: column j + 1 is in flight during column j
-#pragma unroll 1
+T1_HOT_UNROLL
       for (int j = 0; j < n; j++) {
         const double2 a0 = n0, a1 = n1, a2 = n2;
         if (j + 1 < n) { n0 = trow[3 * j + 3]; n1 = trow[3 * j + 4]; n2 = trow[3 * j + 5]; }
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
 #pragma unroll
     for (int e = 0; e < 21; e++) Ap[e] = 0.0;
     unsigned free_mask = 0;
-#pragma unroll 1
+T1_HOT_UNROLL
     for (int j = 0; j < n; j++) {
       const double2 a0 = crow[3 * j + 0], a1 = crow[3 * j + 1], a2 = crow[3 * j + 2];
       const double c[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
@@ -608,7 +618,7 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     for (int a = 0; a < 6; a++) Ap[a * (a + 1) / 2 + a] = Ap[a * (a + 1) / 2 + a] + lambda;
     double y[6];
     ldl6_solve(Ap, rc, y);
-#pragma unroll 1
+T1_HOT_UNROLL
     for (int j = 0; j < n; j++) {
       const double2 a0 = crow[3 * j + 0], a1 = crow[3 * j + 1], a2 = crow[3 * j + 2];
       const double m = ((free_mask >> j) & 1u) ? 1.0 : 0.0;
@@ -728,20 +738,28 @@ static int t1_smem_bytes(int n) {
   return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * ROWS * T1_THREADS * units +
                sizeof(double) * 2 * n * T1_THREADS + sizeof(double) * 4 * n);
 }
-template <bool GENERAL, int ROWS>
+template <bool GENERAL, int ROWS, int NS>
 static int t1_launch(const SolveParams* p, int blocks, cudaStream_t s) {
   const int smem = t1_smem_bytes<GENERAL, ROWS>(p->n);
-  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  solve_t1_kernel<GENERAL, ROWS><<<blocks, T1_THREADS, smem, s>>>(*p);
+  solve_t1_kernel<GENERAL, ROWS, NS><<<blocks, T1_THREADS, smem, s>>>(*p);
   return (int)cudaGetLastError();
+}
+// revolute chains with unit weights and 6 or 7 joints (the common arms) run instances with the joint count baked in
+template <int ROWS>
+static int t1_dispatch(const SolveParams* p, int general, int blocks, cudaStream_t s) {
+  if (general) return t1_launch<true, ROWS, 0>(p, blocks, s);
+  if (p->n == 7) return t1_launch<false, ROWS, 7>(p, blocks, s);
+  if (p->n == 6) return t1_launch<false, ROWS, 6>(p, blocks, s);
+  return t1_launch<false, ROWS, 0>(p, blocks, s);
 }
 template <bool GENERAL, int ROWS>
 static int t1_occupancy(int n, int* blocks_per_sm) {
   const int smem = t1_smem_bytes<GENERAL, ROWS>(n);
-  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_t1_kernel<GENERAL, ROWS>, T1_THREADS, smem);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_t1_kernel<GENERAL, ROWS, 0>, T1_THREADS, smem);
 }
 
 }  // namespace optik
@@ -749,8 +767,7 @@ static int t1_occupancy(int n, int* blocks_per_sm) {
 // general = the chain has a prismatic joint or the config has non-unit weights; rows = 1 or 2 (see the file header)
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows, int blocks, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows == 1) return general ? optik::t1_launch<true, 1>(p, blocks, s) : optik::t1_launch<false, 1>(p, blocks, s);
-  return general ? optik::t1_launch<true, 2>(p, blocks, s) : optik::t1_launch<false, 2>(p, blocks, s);
+  return rows == 1 ? optik::t1_dispatch<1>(p, general, blocks, s) : optik::t1_dispatch<2>(p, general, blocks, s);
 }
 extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
   return rows == 1 ? optik::t1_occupancy<false, 1>(n, blocks_per_sm) : optik::t1_occupancy<false, 2>(n, blocks_per_sm);
