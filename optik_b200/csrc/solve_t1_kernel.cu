@@ -37,7 +37,10 @@
 
 namespace optik {
 
-constexpr int T1_THREADS = 128;
+#ifndef OPTIK_T1_THREADS
+#define OPTIK_T1_THREADS 128
+#endif
+constexpr int T1_THREADS = OPTIK_T1_THREADS;  // threads per block
 constexpr unsigned FULLMASK = 0xffffffffu;
 constexpr unsigned DYN_NONE = 0xffffffffu;
 
@@ -144,7 +147,7 @@ DEV void warp_prefetch(const void* p, unsigned long long bytes, int lane) {
 }
 
 template <bool GENERAL, int ROWS, int NS>
-__global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel(const __grid_constant__ SolveParams P) {
+__global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_THREADS)) solve_t1_kernel(const __grid_constant__ SolveParams P) {
   extern __shared__ __align__(128) double smem[];
   const int n = NS ? NS : P.n;  // NS: the joint count as a compile-time constant (joint loops fully unrolled), 0 = any
   // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[ROWS][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
@@ -215,7 +218,8 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
     const unsigned need = __ballot_sync(FULLMASK, !running && !done);
     if (need) {
       const bool idle = !running && !done;
-      const bool late = P.max_ns && (globaltimer_ns() - t_start) > P.max_ns;  // lib.rs:260-264
+      // lib.rs:260-264; warp-uniform (the timer is read per lane): the branches below hold warp-level primitives
+      const bool late = P.max_ns && __any_sync(FULLMASK, (globaltimer_ns() - t_start) > P.max_ns);
       bool got = false;
       if (sched == 2) {
         unsigned long long nb;
@@ -302,6 +306,33 @@ __global__ void __launch_bounds__(T1_THREADS, ROWS == 1 ? 3 : 2) solve_t1_kernel
           }
           if (pool_next >= P.T) wfd = true;
           want = __ballot_sync(FULLMASK, idle && !got);
+        }
+        // (B2) speculation inside the warp: once every target has been taken, lanes left without work join the chains
+        // that still run in THIS warp and claim the next restarts of their targets in parallel (idle lane number i
+        // helps chain number i mod #chains).  Nothing waits for a failure: the geometric tail of unlucky targets
+        // (one attempt after the other) becomes a few rounds of parallel restarts on lanes that had nothing to do.
+        // A helper's restart index is above its owner's, so it is dropped at the next poll if the owner converges.
+        if (want && wfd && !late) {
+          const unsigned chains = __ballot_sync(FULLMASK, running && job_open);
+          if (chains) {
+            const unsigned nch = __popc(chains), k = __popc(want);
+            const unsigned below = (1u << lane) - 1u;
+            const bool owner = (chains >> lane) & 1u;
+            if (owner && __popc(chains & below) < k && excl) {  // my target gets a helper: it is shared from here on
+              atomicExch(P.dyn_next + tgt_id, my_next);
+              __threadfence();
+              excl = false;
+            }
+            __syncwarp();
+            const bool helper = idle && !got;
+            const int src = helper ? (int)__fns(chains, 0, (__popc(want & below) % nch) + 1) : lane;
+            const unsigned long long ht = __shfl_sync(FULLMASK, tgt_id, src);
+            if (helper && *((volatile unsigned*)(P.dyn_found + ht)) == DYN_NONE) {
+              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + ht, 1u);
+              if (rel < nrest) { tgt_id = ht; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; }
+            }
+            want = __ballot_sync(FULLMASK, idle && !got);
+          }
         }
         // (C) help tickets, one pop of k tickets per warp
         if (want && wfd && !late) {
@@ -769,6 +800,7 @@ extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows
   cudaStream_t s = (cudaStream_t)stream;
   return rows == 1 ? optik::t1_dispatch<1>(p, general, blocks, s) : optik::t1_dispatch<2>(p, general, blocks, s);
 }
+extern "C" int optik_solve_t1_threads(void) { return optik::T1_THREADS; }
 extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
   return rows == 1 ? optik::t1_occupancy<false, 1>(n, blocks_per_sm) : optik::t1_occupancy<false, 2>(n, blocks_per_sm);
 }

@@ -24,6 +24,13 @@ if which == "step":
         cnt = torch.zeros(3, dtype=torch.int64, device=dev)
         r.ik_attempts(cfg, targets[0], x0, 65536, best=True, variant=v, counters=cnt)
     json.dump({"attempts": int(cnt[0]), "evaluations": int(cnt[1]), "converged": int(cnt[2])}, open("gpurun_out/r02_step_counters.json", "w"))
+elif which == "steady":  # 1 Mi seeds to one target: steady state of both layouts (launches 3 and 4 are the ones to capture)
+    qstar = torch.from_numpy(rng.uniform(lb, ub, size=(4, 7))).to(dev)
+    targets = r.eval_batch(qstar, want=("ee",))["ee"].contiguous()
+    x0 = torch.from_numpy(0.5 * (lb + ub)).to(dev)
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=1 << 20)
+    for v in (1, 2, 1, 2):
+        r.ik_attempts(cfg, targets[0], x0, 1 << 20, best=True, variant=v)
 elif which == "snake":
     snake = ob.Robot.named("snake20")
     lbs, ubs = map(np.array, snake.joint_limits())
