@@ -32,7 +32,13 @@ import numpy as np  # noqa: E402
 SEEDS_PER_GPU = 65536
 MIN_TIMED_SECONDS = 1.0
 CPU_BASELINE_PASSES = 32  # cpu_baseline sample: 32 full passes (2 Mi attempts, ~20 CPU-seconds on 16 cores)
-E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "2"))  # host-buffer calls in flight on one GPU
+E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "8"))  # host-buffer calls in flight on one GPU
+# e2e throughput mode: every pass is launched on a FRACTION of the machine (opts.blocks = SMs / E2E_SM_DIV, one block per
+# SM on every other SM's worth of slots) so that several passes are co-resident and one pass's straggler tail runs under
+# the next passes' bulk (measured on B200, tools/exp_e2e.py: full-machine launches 0.208 ms/pass at any depth, half of the
+# SMs' blocks with 8 passes in flight 0.150 ms/pass; the device-timed `value` stays the isolated full-machine pass)
+E2E_SM_DIV = int(os.environ.get("OPTIK_BENCH_E2E_SM_DIV", "2"))
+PT_DEPTH = 3  # per_target e2e: host-buffer batch calls in flight
 E2E_DEPTH_MULTI = 4  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
 TOL_F = 1e-6
@@ -258,13 +264,13 @@ def per_target_block(ob, robot, dev, flush, rank, world, cpu):
     tg, x0, lb, ub = device_targets(robot, ROBOT, T, 1000 + rank, dev)
     ms, ver, claimed = timed_batch(robot, cfg, tg, x0, lb, ub, R, flush)
     n = robot.num_positions()
-    # e2e: pinned host buffers, H2D of targets + seeds and D2H of q / cost / status inside the timed region, two calls in
-    # flight on two library streams (OPTIK_BATCH_ASYNC)
+    # e2e: pinned host buffers, H2D of targets + seeds and D2H of q / cost / status inside the timed region, PT_DEPTH calls
+    # in flight, each on its own library stream (OPTIK_BATCH_ASYNC)
     tg_h, x0_h = ob.pinned_empty((T, 8)), ob.pinned_empty((T, n))
     tg_h[:] = tg.cpu().numpy()
     x0_h[:] = x0.cpu().numpy()
-    sets = [((ob.pinned_empty((T, n)), ob.pinned_empty(T), ob.pinned_empty(T, np.int32)), ob.Stream(robot)) for _ in range(2)]
-    steps = 6
+    sets = [((ob.pinned_empty((T, n)), ob.pinned_empty(T), ob.pinned_empty(T, np.int32)), ob.Stream(robot)) for _ in range(PT_DEPTH)]
+    steps = 12
     solved = 0
 
     def finish(k):
@@ -272,18 +278,18 @@ def per_target_block(ob, robot, dev, flush, rank, world, cpu):
         stream.synchronize()
         return int(cfg.is_success(out[2]).sum())
 
-    for k in range(2):  # warm the streams / pools
+    for k in range(PT_DEPTH):  # warm the streams / pools
         robot.ik_batch(cfg, tg_h, x0_h, restarts=R, out=sets[k][0], stream=sets[k][1], wait=False)
-    for k in range(2):
+    for k in range(PT_DEPTH):
         finish(k)
     t0 = time.perf_counter()
     for s in range(steps):
-        k = s % 2
-        if s >= 2:
+        k = s % PT_DEPTH
+        if s >= PT_DEPTH:
             solved += finish(k)
         robot.ik_batch(cfg, tg_h, x0_h, restarts=R, out=sets[k][0], stream=sets[k][1], wait=False)
-    for s in range(steps - 2, steps):
-        solved += finish(s % 2)
+    for s in range(steps - PT_DEPTH, steps):
+        solved += finish(s % PT_DEPTH)
     e2e_s = time.perf_counter() - t0
     blk = {
         "workload": f"Panda 7-DOF, {T} independent reachable targets per GPU (uniform seeds), SolutionMode::Speed, <= {R} "
@@ -557,6 +563,7 @@ def run_product(args):
         dist.barrier()
     e2e_conv = 0
     D = E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI
+    e2e_blocks = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // E2E_SM_DIV) if (tile or 1) == 1 else 0
     if world == 1 or px is not None:
         while len(sets) < D:
             sets.append(((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
@@ -569,7 +576,7 @@ def run_product(args):
             hrec, hrecord, stream = sets[k]
             push = px.next_push() if world > 1 else None
             robot.ik_attempts(cfg, tg_host[s], x0_host, R, restart_begin=rank * R, tile=tile, best=True, out=hrec,
-                              record=hrecord, stream=stream, wait=False, push=push)
+                              record=hrecord, stream=stream, wait=False, push=push, blocks=e2e_blocks)
             if world > 1:
                 with torch.cuda.stream(ext[k]):
                     px.select(d_best[k], push[3])
@@ -714,6 +721,7 @@ def run_product(args):
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * Pn, "d2h_bytes_per_step": d2h * Pn,
                     "h2d_bytes_per_pass": h2d, "d2h_bytes_per_pass": d2h,
                     "passes": Ke, "ms_per_pass": e2e_s / Ke * 1e3, "pipeline_depth": E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI,
+                    "blocks_per_pass": e2e_blocks,
                     "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
                             "OPTIK_BATCH_ASYNC (C ABI), one stream + buffer set per call in flight; host reads every pass's records"
                             if world == 1 else

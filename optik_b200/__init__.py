@@ -510,7 +510,8 @@ class Robot:
         return (q, f, st, extra) if stats else (q, f, st)
 
     def ik_attempts(self, config, target, x0, restarts, restart_begin=0, tile=0, max_evals=0, ee_offset=None,
-                    best=False, out=None, counters=None, record=None, stream=None, wait=True, variant=0, push=None):
+                    best=False, out=None, counters=None, record=None, stream=None, wait=True, variant=0, push=None,
+                    blocks=0):
         """Per-restart records for one target: (q_all (R,n), f_all, status_all, evals_all), every restart run to
         completion (no Speed-mode early exit) -- BASELINE config 2's output.  best=True also runs the selection
         pass (lib.rs:397-413) and appends the packed candidate record (RECORD_HEAD + n doubles:
@@ -521,7 +522,7 @@ class Robot:
         lib = load_library()
         c = config._c()
         n, R = self._n, int(restarts)
-        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, 0, ee_offset, variant)
+        o, keep = self._opts(0, R, restart_begin, 0, tile, max_evals, blocks, ee_offset, variant)
         if _is_torch(target):
             import torch
             dev = target.device

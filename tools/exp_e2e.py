@@ -21,12 +21,13 @@ targets = robot.eval_batch(qstar, want=("ee",))["ee"].contiguous()
 cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
 tg_host = ob.pinned_empty((Ke, 8)); tg_host[:] = targets.cpu().numpy()
 x0_host = ob.pinned_empty(n); x0_host[:] = 0.5 * (lb + ub)
+BLOCKS = int(os.environ.get("OPTIK_EXP_BLOCKS", "0"))
 for D in [int(a) for a in sys.argv[1:]] or [2, 3, 4]:
     sets = [((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
              ob.pinned_empty(obd.RECORD_HEAD + n), ob.Stream(robot)) for _ in range(D)]
     def submit(s, k):
         hrec, hrecord, stream = sets[k]
-        robot.ik_attempts(cfg, tg_host[s], x0_host, R, best=True, out=hrec, record=hrecord, stream=stream, wait=False)
+        robot.ik_attempts(cfg, tg_host[s], x0_host, R, best=True, out=hrec, record=hrecord, stream=stream, wait=False, blocks=BLOCKS)
     def done(k):
         sets[k][2].synchronize()
         return int((sets[k][0][2] == 1).sum())
@@ -40,4 +41,4 @@ for D in [int(a) for a in sys.argv[1:]] or [2, 3, 4]:
         submit(s, k)
     for s in range(max(Ke - D, 0), Ke): conv += done(s % D)
     dt = time.perf_counter() - t0
-    print(f"{os.path.basename(ob.LIB_PATH)} depth {D}: {dt / Ke * 1e3:.4f} ms/pass  e2e {conv / dt:.4e} converged attempts/s", flush=True)
+    print(f"{os.path.basename(ob.LIB_PATH)} blocks {BLOCKS} depth {D}: {dt / Ke * 1e3:.4f} ms/pass  e2e {conv / dt:.4e} converged attempts/s", flush=True)
