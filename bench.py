@@ -39,7 +39,7 @@ E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "8"))  # host-buf
 # SMs' blocks with 8 passes in flight 0.150 ms/pass; the device-timed `value` stays the isolated full-machine pass)
 E2E_SM_DIV = int(os.environ.get("OPTIK_BENCH_E2E_SM_DIV", "2"))
 PT_DEPTH = 3  # per_target e2e: host-buffer batch calls in flight
-E2E_DEPTH_MULTI = 4  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
+E2E_DEPTH_MULTI = 8  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
 TOL_F = 1e-6
 METRIC = "IK solves/sec (success-gated, Panda 7-DOF)"

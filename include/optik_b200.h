@@ -258,7 +258,7 @@ int optik_gpu_select_records(const optik_robot* robot, const double* records, ui
  *   push    stores `record` into row `rank` of every peer's buffer and raises that row's flag to seq
  *   select  waits (bounded, 2 s) for all `world` rows of call seq in the local buffer and applies the selection rule;
  *           best_record_out[0] = -1 if a peer never delivered
- * Both are asynchronous on `stream`; at most 4 calls may be in flight per rank (8 slots). */
+ * Both are asynchronous on `stream`; at most 16 calls may be in flight per rank (32 slots). */
 uint64_t optik_gpu_exchange_bytes(const optik_robot* robot, uint32_t world);
 int optik_gpu_exchange_push(const optik_robot* robot, const double* record, const uint64_t* peer_buffers_dev, uint32_t rank,
                             uint32_t world, uint64_t seq, void* stream);

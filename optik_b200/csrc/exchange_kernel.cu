@@ -9,16 +9,19 @@
 //           selection rule to the W rows: converged first, lowest score, lowest restart index
 // The payload is 15 doubles per rank: the cost of the exchange is launch + one NVLink round trip (~ a few us) where
 // ncclAllGather costs a kernel launch plus its protocol (~40 us at 8 GPUs, profiles/r01b).  A rank can be at most
-// `pipeline depth` sequence numbers ahead of a peer (its own select for seq needs every peer's push of seq), so NSLOT = 8
-// slots are never overwritten before they are read for depth <= 4.  The wait is bounded (2 s): a dead peer yields
+// `pipeline depth` sequence numbers ahead of a peer (its own select for seq needs every peer's push of seq, and a peer
+// submits seq + depth only after its own select of seq), so NSLOT = 32 slots are never overwritten before they are read
+// for depth <= 16.  The wait is bounded (2 s): a dead peer yields
 // found = -1 in the output record instead of a hung GPU.
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
+#include "solver_params.h"
+
 namespace optik {
 
-constexpr int EX_NSLOT = 8;
+constexpr int EX_NSLOT = OPTIK_EXCHANGE_NSLOT;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

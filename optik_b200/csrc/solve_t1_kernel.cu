@@ -731,8 +731,8 @@ T1_HOT_UNROLL
         else if (tid == 4) v = (double)(((volatile int*)P.cand_status)[win] & 0xff);
         else if (tid >= 8 && tid < len) v = ((volatile double*)P.cand_q)[win * n + (tid - 8)];
         if (tid < len) P.fused_record[tid] = v;
-        if (P.push_peers) {  // cross-GPU: row `push_rank` of slot push_seq % 8 in every peer's buffer, then its flag
-          const unsigned slot = (unsigned)(P.push_seq % 8ull);
+        if (P.push_peers) {  // cross-GPU: row `push_rank` of slot push_seq % NSLOT in every peer's buffer, then its flag
+          const unsigned slot = (unsigned)(P.push_seq % (unsigned long long)OPTIK_EXCHANGE_NSLOT);
           for (int p = 0; p < P.push_world; p++) {
             double* base = (double*)P.push_peers[p];
             if (tid < len) base[((size_t)slot * P.push_world + P.push_rank) * len + tid] = v;
@@ -740,7 +740,7 @@ T1_HOT_UNROLL
           __threadfence_system();
           __syncwarp();
           if (tid < P.push_world) {
-            unsigned long long* flags = (unsigned long long*)((double*)P.push_peers[tid] + (size_t)8 * P.push_world * len);
+            unsigned long long* flags = (unsigned long long*)((double*)P.push_peers[tid] + (size_t)OPTIK_EXCHANGE_NSLOT * P.push_world * len);
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags + (size_t)slot * P.push_world + P.push_rank), "l"(P.push_seq) : "memory");
           }
         }

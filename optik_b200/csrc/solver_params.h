@@ -4,6 +4,8 @@
 
 #define OPTIK_MAX_DOF 32
 #define OPTIK_CHAIN_STRIDE 16 /* doubles per joint in the flat chain */
+/* slots of the cross-GPU exchange buffer (csrc/exchange_kernel.cu): a rank may keep NSLOT / 2 calls in flight */
+#define OPTIK_EXCHANGE_NSLOT 32
 
 // Attempt status (one restart).  1..3 map to NLopt's SuccessState as the
 // reference classifies them (crates/optik/src/lib.rs:376-379).

@@ -176,7 +176,7 @@ class HostStepPipeline:
     def __init__(self, robot, config, restarts_per_rank, rank=0, world=1, group=None, tile=0, depth=2, device=None,
                  exchange=None):
         import torch
-        assert exchange is None or depth <= 4, "the peer exchange keeps at most 4 calls in flight"
+        assert exchange is None or depth <= 16, "the peer exchange keeps at most 16 calls in flight"
         self.exchange = exchange
         self.robot, self.config, self.R, self.rank, self.world, self.group, self.tile = robot, config, int(restarts_per_rank), rank, world, group, tile
         n = robot.num_positions()

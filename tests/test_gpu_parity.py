@@ -852,7 +852,7 @@ def test_solve_against_slsqp_standin(name, R):
 def test_peer_exchange_kernels_single_gpu():
     """optik_gpu_exchange_push / _select (the NVLink best-pick exchange) with four simulated ranks on one GPU: each
     'rank' owns a buffer, every push lands in every buffer, every select returns the record the torch specification of
-    the rule (dist.select_candidates) picks; sequence numbers reuse the 8 slots; a missing peer times out as found=-1."""
+    the rule (dist.select_candidates) picks; sequence numbers reuse the 32 slots; a missing peer times out as found=-1."""
     import torch
     from optik_b200 import dist as obd
     r, ch = robot_and_chain("panda")
@@ -860,12 +860,12 @@ def test_peer_exchange_kernels_single_gpu():
     W, n = 4, ch.n
     L = obd.RECORD_HEAD + n
     nbytes = int(lib.optik_gpu_exchange_bytes(r._h, W))
-    assert nbytes == 8 * W * (L * 8 + 8)
+    assert nbytes == 32 * W * (L * 8 + 8)
     bufs = [torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda") for _ in range(W)]
     peers = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
     rng = np.random.default_rng(3)
     stream = torch.cuda.current_stream().cuda_stream
-    for seq in range(1, 20):
+    for seq in range(1, 70):
         recs = []
         for w in range(W):
             found = float(rng.random() < 0.7)
@@ -878,11 +878,11 @@ def test_peer_exchange_kernels_single_gpu():
             out = torch.empty(L, dtype=torch.float64, device="cuda")
             ob._check(lib.optik_gpu_exchange_select(r._h, bufs[w].data_ptr(), W, seq, out.data_ptr(), stream))
             assert torch.equal(out, ref), (seq, w)
-    # only three of four ranks push sequence 20: the select gives up after its bounded wait
+    # only three of four ranks push sequence 70: the select gives up after its bounded wait
     for w in range(3):
-        ob._check(lib.optik_gpu_exchange_push(r._h, recs[w].data_ptr(), peers.data_ptr(), w, W, 20, stream))
+        ob._check(lib.optik_gpu_exchange_push(r._h, recs[w].data_ptr(), peers.data_ptr(), w, W, 70, stream))
     out = torch.empty(L, dtype=torch.float64, device="cuda")
-    ob._check(lib.optik_gpu_exchange_select(r._h, bufs[0].data_ptr(), W, 20, out.data_ptr(), stream))
+    ob._check(lib.optik_gpu_exchange_select(r._h, bufs[0].data_ptr(), W, 70, out.data_ptr(), stream))
     torch.cuda.synchronize()
     assert out[0].item() == -1.0
 
