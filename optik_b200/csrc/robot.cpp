@@ -513,7 +513,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   }
   {  // warp-level job pools: large enough to amortise the queue atomic, small enough to keep the tail balanced
     const unsigned long long warps = (unsigned long long)plan.blocks * (unsigned long long)(plan.tile == 1 ? optik_solve_t1_threads() / 32 : 4);
-    unsigned long long chunk = (dyn ? T : njobs) / (warps * 8ull);
+    unsigned long long chunk = (dyn ? T * (unsigned long long)(P.dyn_k0 + 1u) : njobs) / (warps * 8ull);
     P.pool_chunk = (unsigned)(chunk < 1 ? 1 : (chunk > 64 ? 64 : chunk));
   }
   if (plan.tile == 1) CUDA_TRY(optik_launch_solve_t1(&P, (P.has_prismatic || P.weighted) ? 1 : 0, rows, plan.blocks, s));

@@ -191,17 +191,21 @@ __global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_TH
   const bool speed = (P.mode == 2);
   const unsigned long long t_start = P.max_ns ? globaltimer_ns() : 0ull;
   const unsigned long long nrest = P.r_end - P.r_begin;
+  // dynamic chains: jobs of the queue and the offset of the shared restart counters (see the transition code)
+  const unsigned long long dyn_jobs = P.T * (unsigned long long)(P.dyn_k0 + 1u), dyn_base = P.dyn_k0 ? P.dyn_k0 + 1u : 0u;
 
   // ---- per-thread state.  sched 0: a "job" is one (target, chunk); sched 1: a "chain" on one target; sched 2: one attempt
   unsigned long long job = 0, tgt_id = 0, r_idx = 0, r_next = 0;
   bool running = false, job_open = false, best_has = false, rec_any = false, done = false;
   bool seed_clamped = false;  // this attempt started from a caller seed that had to be clamped into the limits
+  bool no_help = false; // dynamic: my chain cannot use helpers any more (no restart left / a restart of the target converged)
   bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
   unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
   int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
   unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
   unsigned n_help = 1;  // warp-uniform: tickets a failing chain pushes
+  unsigned help_next = 0, help_gap = 1;  // warp-uniform: pass of the next look for help work, current back-off
   unsigned long long pool_next = 0, pool_end = 0;  // warp-uniform: this warp's claimed range of the job queue
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
@@ -271,40 +275,37 @@ __global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_TH
           if (excl) {  // nobody else knows this target: its restart counter lives in a register
             if (!late && my_next < nrest) { r_idx = P.r_begin + my_next; my_next++; got = true; }
           } else if (!late && *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE) {
-            const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + tgt_id, 1u);
+            const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + tgt_id, 1u);
             if (rel < nrest) { r_idx = P.r_begin + rel; got = true; }
           }
           if (!got) job_open = false;  // chain over
         }
-        // (B) fresh targets, one queue fetch per warp
+        // (B) fresh jobs, one queue fetch per warp.  Job f = first restart of target f; with fewer targets than
+        // resident lanes (dyn_k0 > 0) the queue holds (dyn_k0 + 1) jobs per target -- job f = restart f / T of target
+        // f % T -- so that every lane starts a restart at once (the counter next[t] then counts from dyn_k0 + 1)
         unsigned want = __ballot_sync(FULLMASK, idle && !got);
         if (want && !wfd) {
           unsigned long long nb;
           const unsigned long long f = warp_take(P.queue, lane, want, P.pool_chunk, pool_next, pool_end, nb);
-          if (nb < P.T) {  // the new range's seeds and targets -> L1
+          if (P.dyn_k0 == 0 && nb < P.T) {  // the new range's seeds and targets -> L1
             warp_prefetch(P.x0 + nb * n, (pool_end - nb) * n * sizeof(double), lane);
             warp_prefetch(P.targets + nb * 8, (pool_end - nb) * 64, lane);
           }
-          if (idle && !got) {
-            if (f < P.T) {
-              tgt_id = f;
-              if (late) {  // past the deadline: the target's record says that nothing ran
-                for (int j = 0; j < n; j++) P.cand_q[f * n + j] = P.x0[f * n + j];
-                P.cand_f[f] = 0.0; P.cand_status[f] = OPTIK_ST_SKIPPED;
-                if (P.cand_restart) P.cand_restart[f] = P.r_begin;
-              } else if (nrest > 0) {
-                r_idx = P.r_begin; got = true; job_open = true;
-                excl = P.dyn_k0 == 0;
-                my_next = 1;
-                if (!excl) {  // fewer targets than resident lanes: tickets for parallel chains from the start
-                  atomicExch(P.dyn_next + f, 1u);
-                  __threadfence();
-                  for (unsigned k = 0; k < P.dyn_k0; k++) help_push(P, (unsigned)f);
-                }
+          if (idle && !got && f < dyn_jobs) {
+            const unsigned long long t = P.dyn_k0 ? f % P.T : f, rel0 = P.dyn_k0 ? f / P.T : 0ull;
+            if (late) {  // past the deadline: the target's record says that nothing ran
+              if (rel0 == 0) {
+                for (int j = 0; j < n; j++) P.cand_q[t * n + j] = P.x0[t * n + j];
+                P.cand_f[t] = 0.0; P.cand_status[t] = OPTIK_ST_SKIPPED;
+                if (P.cand_restart) P.cand_restart[t] = P.r_begin;
               }
+            } else if (rel0 < nrest) {
+              tgt_id = t; r_idx = P.r_begin + rel0; got = true; job_open = true; no_help = false;
+              excl = P.dyn_k0 == 0;
+              my_next = 1;
             }
           }
-          if (pool_next >= P.T) wfd = true;
+          if (pool_next >= dyn_jobs) wfd = true;
           want = __ballot_sync(FULLMASK, idle && !got);
         }
         // (B2) speculation inside the warp: once every target has been taken, lanes left without work join the chains
@@ -312,8 +313,11 @@ __global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_TH
         // helps chain number i mod #chains).  Nothing waits for a failure: the geometric tail of unlucky targets
         // (one attempt after the other) becomes a few rounds of parallel restarts on lanes that had nothing to do.
         // A helper's restart index is above its owner's, so it is dropped at the next poll if the owner converges.
+        // Looking for help work costs global round trips that the warp's RUNNING lanes wait for.  A chain whose target
+        // has no restart left or has a converged restart cannot use helpers any more: it is marked (no_help) and left
+        // alone, so every failed claim below happens once.
         if (want && wfd && !late) {
-          const unsigned chains = __ballot_sync(FULLMASK, running && job_open);
+          const unsigned chains = __ballot_sync(FULLMASK, running && job_open && !no_help);
           if (chains) {
             const unsigned nch = __popc(chains), k = __popc(want);
             const unsigned below = (1u << lane) - 1u;
@@ -327,15 +331,23 @@ __global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_TH
             const bool helper = idle && !got;
             const int src = helper ? (int)__fns(chains, 0, (__popc(want & below) % nch) + 1) : lane;
             const unsigned long long ht = __shfl_sync(FULLMASK, tgt_id, src);
-            if (helper && *((volatile unsigned*)(P.dyn_found + ht)) == DYN_NONE) {
-              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + ht, 1u);
-              if (rel < nrest) { tgt_id = ht; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; }
+            bool refused = false;
+            if (helper) {
+              refused = true;
+              if (*((volatile unsigned*)(P.dyn_found + ht)) == DYN_NONE) {
+                const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + ht, 1u);
+                if (rel < nrest) { tgt_id = ht; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; no_help = false; refused = false; }
+              }
             }
+            if ((__reduce_or_sync(FULLMASK, refused ? (1u << src) : 0u) >> lane) & 1u) no_help = true;
             want = __ballot_sync(FULLMASK, idle && !got);
           }
         }
         // (C) help tickets, one pop of k tickets per warp
-        if (want && wfd && !late) {
+        // (polled with a back-off of 2, 4, 8 passes while lanes of this warp run: the poll is two global loads)
+        const bool look = want && wfd && !late && (pass >= help_next || !__any_sync(FULLMASK, running));
+        const unsigned want0 = want;
+        if (look) {
           const int leader = __ffs(want) - 1;
           unsigned long long h = 0;
           unsigned k = 0;
@@ -353,13 +365,17 @@ __global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_TH
           if (idle && !got && rank < k) {
             const unsigned v = atomicExch(P.help_slots + (unsigned)((h + rank) & P.help_mask), 0u);
             if (v && *((volatile unsigned*)(P.dyn_found + (v - 1u))) == DYN_NONE) {
-              const unsigned long long rel = (unsigned long long)atomicAdd(P.dyn_next + (v - 1u), 1u);
-              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; }
+              const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + (v - 1u), 1u);
+              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; no_help = false; }
             }
           }
         }
         // leave when nothing is left to do here: all targets taken, no chain in this warp, no ticket for a few polls
         n_idle = __popc(__ballot_sync(FULLMASK, idle && !got));
+        if (look) {  // nobody got a ticket: back off
+          help_gap = (n_idle == __popc(want0)) ? min(help_gap * 2u, 8u) : 1u;
+          help_next = pass + help_gap;
+        }
         n_help = n_idle >= 16 ? 2u : 1u;
         if (wfd) {
           if (__any_sync(FULLMASK, running || got)) idle_polls = 0;

@@ -79,7 +79,7 @@ struct SolveParams {
   // cand_q/f/status/restart[t] directly (cand_evals[t] += evaluations, zeroed by the host; cand_score unused).
   int sched;
   unsigned pool_chunk;                // jobs a warp claims from the queue per atomic (sched 1, 2)
-  unsigned dyn_k0;                    // help tickets pushed when a target is first taken (T < resident lanes)
+  unsigned dyn_k0;                    // T < resident lanes: restarts 0..dyn_k0 of every target are jobs of the queue (start at once)
   unsigned* dyn_next;                 // [T] next relative restart index to claim            (zeroed)
   unsigned* dyn_found;                // [T] lowest converged relative restart index so far  (0xffffffff)
   unsigned* dyn_lock;                 // [T] record lock                                     (zeroed)
