@@ -421,6 +421,7 @@ def run_product(args):
         raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = obd.bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned buffer exists
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)  # (NCCL's own output goes to stderr: main() re-routed fd 1)
@@ -562,6 +563,7 @@ def run_product(args):
     if world > 1:
         dist.barrier()
     e2e_conv = 0
+    host_submit_s = 0.0
     D = E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI
     e2e_blocks = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // E2E_SM_DIV) if (tile or 1) == 1 else 0
     if world == 1 or px is not None:
@@ -598,7 +600,9 @@ def run_product(args):
             k = s % D
             if s >= D:
                 e2e_conv += done(k)
+            ts = time.perf_counter()
             submit(s, k)
+            host_submit_s += time.perf_counter() - ts
         for s in range(max(Ke - D, 0), Ke):
             e2e_conv += done(s % D)
     else:
@@ -721,7 +725,8 @@ def run_product(args):
             "e2e": {"value": e2e_conv / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * Pn, "d2h_bytes_per_step": d2h * Pn,
                     "h2d_bytes_per_pass": h2d, "d2h_bytes_per_pass": d2h,
                     "passes": Ke, "ms_per_pass": e2e_s / Ke * 1e3, "pipeline_depth": E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI,
-                    "blocks_per_pass": e2e_blocks,
+                    "blocks_per_pass": e2e_blocks, "rank0_numa_node": numa_node,
+                    "rank0_host_enqueue_ms_per_pass": host_submit_s / Ke * 1e3, "host_cores": os.cpu_count(),
                     "api": ("Robot.ik_attempts(pinned host buffers, stream=, wait=False) -> optik_gpu_ik_attempts with "
                             "OPTIK_BATCH_ASYNC (C ABI), one stream + buffer set per call in flight; host reads every pass's records"
                             if world == 1 else

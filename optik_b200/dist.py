@@ -66,6 +66,35 @@ def all_gather_records(record, group=None, out=None):
     return out
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and the node's
+    cpulist), before pinned host buffers are allocated: they then live in the memory next to the GPU's PCIe root, and
+    eight ranks' D2H streams do not all cross to one socket.  Returns the node, or None when nothing was changed
+    (single node, unknown topology, cpuset without those CPUs)."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus, dom, dv = pr.pci_bus_id, pr.pci_domain_id, pr.pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dv:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0 or not os.path.isdir(f"/sys/devices/system/node/node{node}"):
+            return None
+        if len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]) < 2:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class PeerExchange:
     """The best-pick exchange as direct peer-to-peer stores over NVLink (optik_gpu_exchange_push / _select,
     csrc/exchange_kernel.cu) instead of an NCCL all-gather: every rank owns one symmetric buffer that torch's symmetric
