@@ -139,8 +139,8 @@ typedef struct optik_gpu_batch_opts {
                               0 = config->max_restarts, which must then be finite and > 0 */
   uint64_t restart_begin;  /* first restart index; [restart_begin, restart_begin+restarts) is run */
   uint32_t chunks;         /* parallel chunks per target (each runs its restarts in index order); 0 = auto */
-  uint32_t tile;           /* lanes per restart seed: 1 = thread-per-seed kernel (n <= 8, batch throughput layout),
-                              8, 16, 32 (= one warp per seed) = tile kernel; 0 = auto (1 if n <= 8, else smallest fit) */
+  uint32_t tile;           /* lanes per restart seed: 1 = thread-per-seed kernel (batch throughput layout),
+                              8, 16, 32 (= one warp per seed) = tile kernel; 0 = auto (1 for batched calls) */
   uint32_t max_evals;      /* objective evaluations per attempt; 0 = default (32) */
   uint32_t blocks;         /* grid size; 0 = auto (multiple of the SM count) */
   int32_t memory;          /* 0: all data pointers are host memory; 1: device memory (async on `stream`) */

@@ -36,7 +36,7 @@ extern "C" int optik_launch_diffik(const DiffIkParams* p, int blocks, void* stre
 extern "C" int optik_eval_occupancy(int n, int cols, int* blocks_per_sm);
 extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows, int blocks, void* stream);
 extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm);
-extern "C" int optik_solve_t1_threads(void);
+extern "C" int optik_solve_t1_threads(int n, int rows);
 extern "C" int optik_launch_seed_table(const double* chain, int n, const uint32_t* key_dev, unsigned long long r_begin,
                                        unsigned long long count, double* out, void* stream);
 extern "C" int optik_launch_chacha8_kat(const uint32_t* key_dev, unsigned long long stream_id, uint32_t* out16_dev, void* stream);
@@ -163,7 +163,7 @@ struct optik_robot {
   mutable uint32_t chain_bytes = 0;
   mutable int sm_count = 0;
   mutable int occ[3] = {0, 0, 0};  // resident blocks/SM for TILE 8,16,32
-  mutable int occ_t1[2] = {0, 0};  // resident blocks/SM of the thread-per-seed kernel (n <= 8): rows = 1, rows = 2
+  mutable int occ_t1[2] = {0, 0};  // resident blocks/SM of the thread-per-seed kernel: rows = 1, rows = 2
   mutable DevBuf scratch;          // single-call scratch (ik / fk / jacobian), guarded by mu
   mutable cudaStream_t stream = nullptr;
   mutable void* pinned = nullptr;
@@ -294,7 +294,7 @@ optik_robot* try_from_urdf_str(const char* urdf, const char* base, const char* e
 struct Plan {
   int tile, blocks, tiles_per_block, resident_tiles, rows;
 };
-// lanes per restart seed: 1 = thread-per-seed kernel (n <= 8), 8/16/32 = tile kernel.  `batch`: auto picks the
+// lanes per restart seed: 1 = thread-per-seed kernel, 8/16/32 = tile kernel.  `batch`: auto picks the
 // throughput layout (1) when it exists, otherwise / for single-target latency the smallest tile that fits.
 int choose_tile(const optik_robot* r, uint32_t want, bool batch) {
   const int n = r->n;
@@ -312,14 +312,14 @@ int t1_rows(const optik_robot* r, const optik_gpu_batch_opts* o, double attempts
   if (o && (o->variant == 1 || o->variant == 2)) return (int)o->variant;
   // three blocks per SM win once every lane runs several attempts (throughput); with about one attempt per lane the
   // launch is a latency chain and two blocks per SM with the trial columns in shared memory are faster
-  const double lanes1 = (double)r->sm_count * (r->occ_t1[0] > 0 ? r->occ_t1[0] : 3) * (double)optik_solve_t1_threads();
+  const double lanes1 = (double)r->sm_count * (r->occ_t1[0] > 0 ? r->occ_t1[0] : 3) * (double)optik_solve_t1_threads(r->n, 1);
   return attempts >= 4.0 * lanes1 ? 1 : 2;
 }
 Plan make_plan(const optik_robot* r, int tile, int rows, uint32_t blocks_req, unsigned long long njobs) {
   Plan p;
   p.tile = tile;
   p.rows = rows;
-  p.tiles_per_block = tile == 1 ? optik_solve_t1_threads() : 128 / tile;
+  p.tiles_per_block = tile == 1 ? optik_solve_t1_threads(r->n, rows) : 128 / tile;
   const int oi = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
   int per_sm = r->occ[oi] > 0 ? r->occ[oi] : 1;
   if (tile == 1) per_sm = r->occ_t1[rows - 1] > 0 ? r->occ_t1[rows - 1] : 1;
@@ -512,7 +512,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     }
   }
   {  // warp-level job pools: large enough to amortise the queue atomic, small enough to keep the tail balanced
-    const unsigned long long warps = (unsigned long long)plan.blocks * (unsigned long long)(plan.tile == 1 ? optik_solve_t1_threads() / 32 : 4);
+    const unsigned long long warps = (unsigned long long)plan.blocks * (unsigned long long)(plan.tile == 1 ? optik_solve_t1_threads(n, rows) / 32 : 4);
     unsigned long long chunk = (dyn ? T * (unsigned long long)(P.dyn_k0 + 1u) : njobs) / (warps * 8ull);
     P.pool_chunk = (unsigned)(chunk < 1 ? 1 : (chunk > 64 ? 64 : chunk));
   }

@@ -1,5 +1,5 @@
-// solve_t1_kernel.cu -- the restart solve with ONE THREAD PER RESTART SEED (throughput layout; any chain whose
-// per-thread rows fit the SM's shared memory: n <= 27 with 128-thread blocks).
+// solve_t1_kernel.cu -- the restart solve with ONE THREAD PER RESTART SEED (throughput layout; any chain of up to 32
+// joints: 128-thread blocks, 32-thread blocks for long chains so that more of their per-thread rows fit an SM).
 //
 // Same path, objective, stop rules, seeds and LM step as solve_kernel.cu (reference: crates/optik/src/lib.rs:297-413,
 // objective.rs:40-110, kinematics.rs:123-196, math.rs:40-203), but the evaluation order is sequential per seed:
@@ -40,7 +40,11 @@ namespace optik {
 #ifndef OPTIK_T1_THREADS
 #define OPTIK_T1_THREADS 128
 #endif
-constexpr int T1_THREADS = OPTIK_T1_THREADS;  // threads per block
+constexpr int T1_THREADS_STD = OPTIK_T1_THREADS;  // threads per block
+// long chains (one-row layout, n > 12): 32-thread blocks.  A 128-thread block of the 20-joint snake needs 166 KB, so one
+// block = 4 warps per SM; five 32-thread blocks (44.8 KB each) fit.
+constexpr int T1_THREADS_LONG = 32;
+constexpr int T1_LONG_N = 12;
 constexpr unsigned FULLMASK = 0xffffffffu;
 constexpr unsigned DYN_NONE = 0xffffffffu;
 
@@ -146,8 +150,9 @@ DEV void warp_prefetch(const void* p, unsigned long long bytes, int lane) {
   }
 }
 
-template <bool GENERAL, int ROWS, int NS>
-__global__ void __launch_bounds__(T1_THREADS, (ROWS == 1 ? 3 : 2) * (128 / T1_THREADS)) solve_t1_kernel(const __grid_constant__ SolveParams P) {
+template <bool GENERAL, int ROWS, int NS, int TB>
+__global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1_kernel(const __grid_constant__ SolveParams P) {
+  constexpr int T1_THREADS = TB;
   extern __shared__ __align__(128) double smem[];
   const int n = NS ? NS : P.n;  // NS: the joint count as a compile-time constant (joint loops fully unrolled), 0 = any
   // layout: chain blob | tip^-1 pose8 | mbarrier (16 B) | rows[ROWS][T1_THREADS][units] (16 B units) | qc[n][T] | qt[n][T] |
@@ -779,34 +784,40 @@ T1_HOT_UNROLL
   }
 }
 
-template <bool GENERAL, int ROWS>
-static int t1_smem_bytes(int n) {
-  const size_t units = (size_t)((3 * n) | 1);
-  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * ROWS * T1_THREADS * units +
-               sizeof(double) * 2 * n * T1_THREADS + sizeof(double) * 4 * n);
+static int t1_threads(int n, int rows) { return (rows == 1 && n > T1_LONG_N) ? T1_THREADS_LONG : T1_THREADS_STD; }
+static int t1_smem_bytes(int n, int rows) {
+  const size_t units = (size_t)((3 * n) | 1), tb = (size_t)t1_threads(n, rows);
+  return (int)(sizeof(double) * (OPTIK_CHAIN_STRIDE * n + 8 + 8 + 2) + 16 * rows * tb * units +
+               sizeof(double) * 2 * n * tb + sizeof(double) * 4 * n);
 }
-template <bool GENERAL, int ROWS, int NS>
+template <bool GENERAL, int ROWS, int NS, int TB>
 static int t1_launch(const SolveParams* p, int blocks, cudaStream_t s) {
-  const int smem = t1_smem_bytes<GENERAL, ROWS>(p->n);
-  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = t1_smem_bytes(p->n, ROWS);
+  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS, NS, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  solve_t1_kernel<GENERAL, ROWS, NS><<<blocks, T1_THREADS, smem, s>>>(*p);
+  solve_t1_kernel<GENERAL, ROWS, NS, TB><<<blocks, TB, smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
 // revolute chains with unit weights and 6 or 7 joints (the common arms) run instances with the joint count baked in
 template <int ROWS>
 static int t1_dispatch(const SolveParams* p, int general, int blocks, cudaStream_t s) {
-  if (general) return t1_launch<true, ROWS, 0>(p, blocks, s);
-  if (p->n == 7) return t1_launch<false, ROWS, 7>(p, blocks, s);
-  if (p->n == 6) return t1_launch<false, ROWS, 6>(p, blocks, s);
-  return t1_launch<false, ROWS, 0>(p, blocks, s);
+  if (t1_threads(p->n, ROWS) == T1_THREADS_LONG) {
+    if (ROWS != 1) return (int)cudaErrorInvalidValue;
+    return general ? t1_launch<true, 1, 0, T1_THREADS_LONG>(p, blocks, s) : t1_launch<false, 1, 0, T1_THREADS_LONG>(p, blocks, s);
+  }
+  if (general) return t1_launch<true, ROWS, 0, T1_THREADS_STD>(p, blocks, s);
+  if (p->n == 7) return t1_launch<false, ROWS, 7, T1_THREADS_STD>(p, blocks, s);
+  if (p->n == 6) return t1_launch<false, ROWS, 6, T1_THREADS_STD>(p, blocks, s);
+  return t1_launch<false, ROWS, 0, T1_THREADS_STD>(p, blocks, s);
 }
-template <bool GENERAL, int ROWS>
-static int t1_occupancy(int n, int* blocks_per_sm) {
-  const int smem = t1_smem_bytes<GENERAL, ROWS>(n);
-  cudaError_t e = cudaFuncSetAttribute(solve_t1_kernel<GENERAL, ROWS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <int ROWS>
+static int t1_occupancy(int n, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
+  const int smem = t1_smem_bytes(n, ROWS);
+  const void* fn = (ROWS == 1 && t1_threads(n, ROWS) == T1_THREADS_LONG) ? (const void*)solve_t1_kernel<false, 1, 0, T1_THREADS_LONG>
+                                                                          : (const void*)solve_t1_kernel<false, ROWS, 0, T1_THREADS_STD>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, solve_t1_kernel<GENERAL, ROWS, 0>, T1_THREADS, smem);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, t1_threads(n, ROWS), smem);
 }
 
 }  // namespace optik
@@ -816,9 +827,9 @@ extern "C" int optik_launch_solve_t1(const SolveParams* p, int general, int rows
   cudaStream_t s = (cudaStream_t)stream;
   return rows == 1 ? optik::t1_dispatch<1>(p, general, blocks, s) : optik::t1_dispatch<2>(p, general, blocks, s);
 }
-extern "C" int optik_solve_t1_threads(void) { return optik::T1_THREADS; }
-extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
-  return rows == 1 ? optik::t1_occupancy<false, 1>(n, blocks_per_sm) : optik::t1_occupancy<false, 2>(n, blocks_per_sm);
+extern "C" int optik_solve_t1_threads(int n, int rows) { return optik::t1_threads(n, rows); }
+extern "C" int optik_solve_t1_occupancy(int n, int rows, int* blocks_per_sm) {
+  return rows == 1 ? optik::t1_occupancy<1>(n, blocks_per_sm) : optik::t1_occupancy<2>(n, blocks_per_sm);
 }
 extern "C" int optik_launch_seed_table(const double* chain, int n, const uint32_t* key_dev, unsigned long long r_begin,
                                        unsigned long long count, double* out, void* stream) {

@@ -22,8 +22,9 @@ def robot_and_chain(name):
 
 def twin_layout(ch, tile=0):
     """Which twin mirrors the kernel the library picks: thread-per-seed (1) for tile=1 or auto in batched calls (every
-    chain whose per-thread rows fit shared memory: n <= 27), else the tile kernel's lane-per-joint order (0)."""
-    return 1 if (tile == 1 or (tile == 0 and ch.n <= 27)) else 0
+    chain: long ones run 32-thread blocks so that their rows fit shared memory), else the tile kernel's
+    lane-per-joint order (0)."""
+    return 1 if tile in (0, 1) else 0
 
 
 def targets_for(ch, rng, T):
@@ -446,8 +447,8 @@ def arm(n, prismatic_at=(), tip=("0 0.05 0.1", "0.3 0 0.2")):
     (4, (0, 3), None, (1, 8, 32)),                           # prismatic first and last
     (1, (), ("0 0 0.2", "0 0 0"), (1, 8)),                   # single joint
     (12, (5,), ("0 0 0.1", "0.1 0 0"), (1, 16, 32)),         # n > 8 (seeds span two ChaCha8 blocks), a prismatic joint
-    (27, (), ("0 0 0.05", "0 0 0"), (1, 32)),                # the longest chain whose rows fit the thread-per-seed kernel
-    (30, (), ("0 0 0.05", "0 0 0"), (0, 32)),                # beyond it: the tile kernel (auto)
+    (27, (), ("0 0 0.05", "0 0 0"), (1, 32)),                # long chains: 32-thread blocks of the thread-per-seed kernel
+    (32, (), ("0 0 0.05", "0 0 0"), (0, 1, 32)),             # the longest chain the library takes (auto = thread per seed)
 ])
 def test_chain_shapes_match_twin_and_oracle(n, pris, tip, tiles):
     urdf, base, ee = arm(n, pris, tip)

@@ -37,6 +37,11 @@ for name in ("panda", "ur5", "snake20"):
         for v in (1, 2):
             qd, fd, sd = r.ik_batch(scfg, tgd, x0d, restarts=8, variant=v)
         assert int(sd[5]) & 0x100
+        # more targets than resident lanes: exclusive chains that turn shared when idle lanes of their warp join them
+        T2 = 40000
+        tg2 = r.eval_batch(torch.from_numpy(rng.uniform(lb, ub, size=(T2, n))).cuda(), want=("ee",))["ee"].contiguous()
+        x02 = torch.from_numpy(rng.uniform(lb, ub, size=(T2, n))).cuda()
+        r.ik_batch(scfg, tg2, x02, restarts=8)
         r.restart_seeds(1, 100)
         r.chacha8_block(np.zeros(8, dtype=np.uint32), 0)
         # Robot::ik fast path (mapped memory, fused selection), default and bounded budgets
