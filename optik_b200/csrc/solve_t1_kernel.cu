@@ -813,6 +813,10 @@ static int t1_dispatch(const SolveParams* p, int general, int blocks, cudaStream
 template <int ROWS>
 static int t1_occupancy(int n, int* blocks_per_sm) {  // same resources for both GENERAL variants' launch bounds
   const int smem = t1_smem_bytes(n, ROWS);
+  int dev = 0, optin = 0;  // a layout that cannot fit is "0 blocks", not an API error
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+    return (int)cudaGetLastError();
+  if (smem > optin) { *blocks_per_sm = 0; return 0; }
   const void* fn = (ROWS == 1 && t1_threads(n, ROWS) == T1_THREADS_LONG) ? (const void*)solve_t1_kernel<false, 1, 0, T1_THREADS_LONG>
                                                                           : (const void*)solve_t1_kernel<false, ROWS, 0, T1_THREADS_STD>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
