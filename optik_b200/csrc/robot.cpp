@@ -424,15 +424,15 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const size_t off_ev = ((direct && d_evals) || dyn) ? 0 : carve(njobs * sizeof(int));
   const bool use_found = speed && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
-  // dynamic chains: [queue | ticket head | ticket tail (one 128-byte line each) | next[T] | lock[T] | ticket ring] zeroed
-  // together, found[T] set to ~0
+  // dynamic chains: [queue | ticket head | ticket tail (one 128-byte line each) | next[T] | ticket ring] zeroed
+  // together, the per-target found / record words [T] set to ~0
   unsigned help_cap = 1;
   if (dyn) while (help_cap < 4u * (unsigned)plan0.resident_tiles) help_cap <<= 1;
-  const size_t dyn_zero = 384 + 2 * T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned);
+  const size_t dyn_zero = 384 + T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned);
   const size_t off_zero = carve(dyn ? dyn_zero : 16);  // static: [queue (8 B) | fused_done (4 B)]
   const bool fused = tile == 1 && per_attempt_records && T == 1 && d_best_record != nullptr;  // selection inside the solve launch
   const size_t off_fpart = fused ? carve((size_t)plan.blocks * 24) : 0;
-  const size_t off_dfound = dyn ? carve(T * sizeof(unsigned)) : 0;
+  const size_t off_dfound = dyn ? carve(T * sizeof(unsigned long long)) : 0;
   // selection: slice the candidate range when one target has very many chunks
   unsigned slices = 1;
   if (C >= 4096) { slices = (unsigned)((C + 1023) / 1024); if (slices > 256) slices = 256; }
@@ -481,15 +481,14 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
     P.sched = 1;
     P.dyn_ctl = (unsigned long long*)(sc + off_zero + 128);
     P.dyn_next = (unsigned*)(sc + off_zero + 384);
-    P.dyn_lock = P.dyn_next + T;
-    P.help_slots = P.dyn_lock + T;
+    P.help_slots = P.dyn_next + T;
     P.help_mask = help_cap - 1;
-    P.dyn_found = (unsigned*)(sc + off_dfound);
+    P.dyn_word = (unsigned long long*)(sc + off_dfound);
     const uint64_t lanes = (uint64_t)plan0.resident_tiles;
     P.dyn_k0 = T >= lanes ? 0u : (unsigned)((lanes + T - 1) / T - 1);
     if (P.dyn_k0 > 7) P.dyn_k0 = 7;
     CUDA_TRY(cudaMemsetAsync(sc + off_zero, 0, dyn_zero, s));
-    CUDA_TRY(cudaMemsetAsync(P.dyn_found, 0xff, T * sizeof(unsigned), s));
+    CUDA_TRY(cudaMemsetAsync(P.dyn_word, 0xff, T * sizeof(unsigned long long), s));
     if (d_evals) CUDA_TRY(cudaMemsetAsync(d_evals, 0, T * sizeof(int32_t), s));
   } else {
     P.sched = (per_attempt_records && tile == 1 && T == 1) ? 2 : 0;

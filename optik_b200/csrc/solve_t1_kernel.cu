@@ -115,6 +115,10 @@ DEV void help_push(const SolveParams& P, unsigned t) {
   atomicExch(P.help_slots + (unsigned)(s & P.help_mask), t + 1u);
 }
 
+// ---- per-target word of the dynamic scheduler: high half = lowest converged relative restart index so far (DYN_NONE:
+// none), low half = 1 while a writer holds the target's record (anything else: free).  Initialised to all ones.
+DEV unsigned dyn_found_of(const SolveParams& P, unsigned long long t) { return ((volatile unsigned*)(P.dyn_word + t))[1]; }
+
 // ---- warp-level job pool.  `mask` = lanes that want a job (warp-uniform).  The pool [pool_next, pool_end) is a range
 // of the global queue claimed `chunk` jobs at a time by ONE atomic, so that most job starts cost no memory round trip;
 // on a refill `nb` is the new range's first job (the caller prefetches its inputs) else ~0.
@@ -203,6 +207,8 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
   unsigned long long job = 0, tgt_id = 0, r_idx = 0, r_next = 0;
   bool running = false, job_open = false, best_has = false, rec_any = false, done = false;
   bool seed_clamped = false;  // this attempt started from a caller seed that had to be clamped into the limits
+  bool pre_ok = false;  // dynamic, shared target: pre_rel is a claimed restart index that may run
+  unsigned long long pre_rel = 0;
   bool no_help = false; // dynamic: my chain cannot use helpers any more (no restart left / a restart of the target converged)
   bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
   unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
@@ -279,10 +285,10 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
         if (idle && job_open) {
           if (excl) {  // nobody else knows this target: its restart counter lives in a register
             if (!late && my_next < nrest) { r_idx = P.r_begin + my_next; my_next++; got = true; }
-          } else if (!late && *((volatile unsigned*)(P.dyn_found + tgt_id)) == DYN_NONE) {
-            const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + tgt_id, 1u);
-            if (rel < nrest) { r_idx = P.r_begin + rel; got = true; }
+          } else if (!late && pre_ok) {  // shared target: the index was claimed when the last attempt failed (one round trip)
+            r_idx = P.r_begin + pre_rel; got = true;
           }
+          pre_ok = false;
           if (!got) job_open = false;  // chain over
         }
         // (B) fresh jobs, one queue fetch per warp.  Job f = first restart of target f; with fewer targets than
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
             bool refused = false;
             if (helper) {
               refused = true;
-              if (*((volatile unsigned*)(P.dyn_found + ht)) == DYN_NONE) {
+              if (dyn_found_of(P, ht) == DYN_NONE) {
                 const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + ht, 1u);
                 if (rel < nrest) { tgt_id = ht; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; no_help = false; refused = false; }
               }
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
           const unsigned rank = __popc(want & ((1u << lane) - 1u));
           if (idle && !got && rank < k) {
             const unsigned v = atomicExch(P.help_slots + (unsigned)((h + rank) & P.help_mask), 0u);
-            if (v && *((volatile unsigned*)(P.dyn_found + (v - 1u))) == DYN_NONE) {
+            if (v && dyn_found_of(P, v - 1u) == DYN_NONE) {
               const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + (v - 1u), 1u);
               if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; no_help = false; }
             }
@@ -520,7 +526,7 @@ T1_HOT_UNROLL
     if (speed && (pass & 3u) == 0u) {
       if (sched == 1) {
         if (status == OPTIK_ST_NONE && !excl &&
-            *((volatile unsigned*)(P.dyn_found + tgt_id)) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
+            dyn_found_of(P, tgt_id) < (unsigned)(r_idx - P.r_begin)) status = OPTIK_ST_SKIPPED;
       } else if (P.found) {
         if (status == OPTIK_ST_NONE && *((volatile unsigned long long*)(P.found + tgt_id)) < r_idx) status = OPTIK_ST_SKIPPED;
       }
@@ -583,36 +589,49 @@ T1_HOT_UNROLL
             // parallel (two when half of this warp's lanes were left without work by the last transition pass; pushing
             // as many tickets as there are idle lanes was measured slower: stale tickets flood the ring).  From here on
             // the target is shared: restart counter, found[] and the record lock live in memory.
-            atomicExch(P.dyn_next + tgt_id, my_next);
+            // (the chain's own next restart is my_next: it goes on with it, the helpers claim from my_next + 1)
+            pre_rel = my_next; pre_ok = true;
+            atomicExch(P.dyn_next + tgt_id, my_next + 1u);
             __threadfence();
             for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
             excl = false;
           }
         } else {
-          // shared target: writers serialise on a per-target lock and re-check found[t] under it, so the row is never
-          // torn and ends as the lowest-index converged attempt
-          bool write = false;
-          if (success) write = atomicMin(P.dyn_found + tgt_id, rel) > rel;
-          else write = (rel == 0u) && status != OPTIK_ST_SKIPPED;
-          if (write) {
-            bool locked = false;
-            while (!locked) {
-              if (atomicCAS(P.dyn_lock + tgt_id, 0u, 1u) == 0u) {
-                const unsigned fnow = *((volatile unsigned*)(P.dyn_found + tgt_id));
-                if (success ? fnow == rel : fnow == DYN_NONE) {
-#pragma unroll 1
-                  for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
-                  P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
-                  if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
-                }
-                __threadfence();
-                atomicExch(P.dyn_lock + tgt_id, 0u);
-                locked = true;
+          // shared target.  A failed attempt claims the chain's next restart and reads found[t] right here -- two
+          // independent requests in flight together with the tickets, consumed by the next transition pass.  A record
+          // is written under the target's word: one CAS takes the record and publishes the index (only a new lowest
+          // index gets it; a higher one sees that and leaves), the row is written, fenced and the word released.
+          if (!success && status != OPTIK_ST_SKIPPED) {
+            const unsigned fnow = dyn_found_of(P, tgt_id);
+            pre_rel = dyn_base + atomicAdd(P.dyn_next + tgt_id, 1u);
+            pre_ok = fnow == DYN_NONE && pre_rel < nrest;
+            if (wfd)
+              for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
+          }
+          if (success || (rel == 0u && status != OPTIK_ST_SKIPPED)) {
+            const unsigned pub = success ? rel : DYN_NONE;  // a failure record leaves found[t] empty
+            unsigned long long w = ~0ull;                   // optimistic: nothing recorded, nobody writing
+            for (;;) {
+              const unsigned f = (unsigned)(w >> 32);
+              if (success ? f <= rel : f != DYN_NONE) break;            // a lower index (any index) is already recorded
+              if ((unsigned)w == 1u) {                                   // a writer holds the record
+                if (!success) break;                                     // ... and it can only be a converged attempt
+                w = *((volatile unsigned long long*)(P.dyn_word + tgt_id));
+                continue;
               }
+              const unsigned long long old = atomicCAS(P.dyn_word + tgt_id, w, ((unsigned long long)pub << 32) | 1ull);
+              if (old == w) {
+#pragma unroll 1
+                for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
+                P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
+                if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
+                __threadfence();
+                *((volatile unsigned long long*)(P.dyn_word + tgt_id)) = (unsigned long long)pub << 32;
+                break;
+              }
+              w = old;
             }
           }
-          if (!success && status != OPTIK_ST_SKIPPED && wfd)
-            for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
         }
       }
       running = false;

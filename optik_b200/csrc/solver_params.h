@@ -81,8 +81,8 @@ struct SolveParams {
   unsigned pool_chunk;                // jobs a warp claims from the queue per atomic (sched 1, 2)
   unsigned dyn_k0;                    // T < resident lanes: restarts 0..dyn_k0 of every target are jobs of the queue (start at once)
   unsigned* dyn_next;                 // [T] next relative restart index to claim            (zeroed)
-  unsigned* dyn_found;                // [T] lowest converged relative restart index so far  (0xffffffff)
-  unsigned* dyn_lock;                 // [T] record lock                                     (zeroed)
+  unsigned long long* dyn_word;       // [T] high half: lowest converged relative restart index so far, low half: 1 while
+                                      //     a writer holds the target's record                  (all ones)
   unsigned long long* dyn_ctl;        // [0] ticket head [1] ticket tail [2] live chains     (zeroed)
   unsigned* help_slots;               // [help_mask + 1] ticket ring, value = target + 1     (zeroed)
   unsigned help_mask;

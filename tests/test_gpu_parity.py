@@ -682,7 +682,8 @@ def test_cpp_consumer_end_to_end(name, tmp_path):
     assert dik == solved  # diff_ik always has a solution (alpha = 0 at worst)
 
 
-@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 6000, 24)])
+@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 6000, 24),
+                                      ("panda", 70000, 32)])
 def test_dynamic_speed_batches_equal_static_schedule(name, T, R):
     """Speed batches run as dynamic chains (restarts claimed on the device, idle lanes help unsolved targets in
     parallel): q, cost, status, winning restart and the per-target success set are identical to the static

@@ -31,6 +31,15 @@ elif which == "steady":  # 1 Mi seeds to one target: steady state of both layout
     cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=1 << 20)
     for v in (1, 2, 1, 2):
         r.ik_attempts(cfg, targets[0], x0, 1 << 20, best=True, variant=v)
+elif which == "mid":  # a mid-size Speed batch (fewer targets than resident lanes: shared chains from the start)
+    T = 16384
+    lb_t, ub_t = torch.from_numpy(lb).to(dev), torch.from_numpy(ub).to(dev)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    qs = torch.rand((T, 7), dtype=torch.float64, device=dev, generator=g) * (ub_t - lb_t) + lb_t
+    x0s = (torch.rand((T, 7), dtype=torch.float64, device=dev, generator=g) * (ub_t - lb_t) + lb_t).contiguous()
+    tg = r.eval_batch(qs, want=("ee",))["ee"].contiguous()
+    for R in (2, 32, 2, 32):
+        r.ik_batch(ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R), tg, x0s, restarts=R)
 elif which == "snake":
     snake = ob.Robot.named("snake20")
     lbs, ubs = map(np.array, snake.joint_limits())
