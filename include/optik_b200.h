@@ -141,8 +141,10 @@ typedef struct optik_gpu_batch_opts {
   uint32_t chunks;         /* parallel chunks per target (each runs its restarts in index order); 0 = auto */
   uint32_t tile;           /* lanes per restart seed: 1 = thread-per-seed kernel (batch throughput layout),
                               8, 16, 32 (= one warp per seed) = tile kernel; 0 = auto (1 for batched calls) */
-  uint32_t max_evals;      /* objective evaluations per attempt; 0 = default (32) */
-  uint32_t blocks;         /* grid size; 0 = auto (multiple of the SM count) */
+  uint32_t max_evals;      /* objective evaluations per attempt; 0 = default (24) */
+  uint32_t blocks;         /* grid size; 0 = auto (one resident wave: a multiple of the SM count).  Asynchronous callers that keep
+                              several calls in flight give each a fraction of the wave (e.g. one block per SM), so that the
+                              calls are co-resident and one call's straggler tail runs under the others' bulk */
   int32_t memory;          /* 0: all data pointers are host memory; 1: device memory (async on `stream`) */
   const double* ee_offset; /* pose8 (host memory) or NULL = identity (lib.rs:245) */
   uint64_t* restart_out;   /* [T] winning restart index, optional (ignored by optik_gpu_ik_attempts: see best_record_out[2]) */
