@@ -270,7 +270,7 @@ def per_target_block(ob, robot, dev, flush, rank, world, cpu):
     tg_h[:] = tg.cpu().numpy()
     x0_h[:] = x0.cpu().numpy()
     sets = [((ob.pinned_empty((T, n)), ob.pinned_empty(T), ob.pinned_empty(T, np.int32)), ob.Stream(robot)) for _ in range(PT_DEPTH)]
-    steps = 12
+    steps = 24
     solved = 0
 
     def finish(k):

@@ -80,3 +80,13 @@ def test_best_pick_exchange_world2_gloo(tmp_path):
             assert a[trial][0] == 1.0 and a[trial][2] == want[2]
         else:
             assert a[trial][0] == 0.0
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    """bind_to_gpu_numa_node never raises and leaves the affinity alone when it cannot resolve the GPU's node (no CUDA
+    device here; single-node hosts)."""
+    import os
+    from optik_b200 import dist as obd
+    before = os.sched_getaffinity(0)
+    assert obd.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
