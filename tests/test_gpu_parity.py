@@ -718,6 +718,23 @@ def test_dynamic_speed_batches_equal_static_schedule(name, T, R):
             assert int(e3["restart"][t]) == ref["restart"] and np.array_equal(q3[t], ref["q"])
 
 
+@pytest.mark.parametrize("name,T,R", [("panda", 12000, 6), ("panda", 38000, 32), ("ur3e", 9000, 64)])
+def test_dynamic_speed_batches_are_repeatable(name, T, R):
+    """Shared targets (record word, restart counters, tickets, in-warp speculation) under repetition: the timing of
+    helpers differs from launch to launch, the per-target answer must not -- 12 launches, both column layouts, each
+    identical to the static schedule (tools/stress_dynamic.py runs the long version)."""
+    import torch
+    r, ch = robot_and_chain(name)
+    tg, x0, lb, ub = _device_targets(r, ch, T, 29)
+    cfg = ob.SolverConfig(solution_mode="speed", max_time=0.0, max_restarts=R)
+    q1, f1, s1, e1 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True, static=True, chunks=1)
+    ok = torch.as_tensor(cfg.is_success(s1.cpu().numpy()), device="cuda")
+    for rep in range(12):
+        q2, f2, s2, e2 = r.ik_batch(cfg, tg, x0, restarts=R, stats=True, variant=1 + rep % 2)
+        assert torch.equal(s1, s2) and torch.equal(q1[ok], q2[ok]) and torch.equal(f1[ok], f2[ok]), rep
+        assert torch.equal(e1["restart"][ok], e2["restart"][ok]) and torch.equal(q1[~ok], q2[~ok]), rep
+
+
 @pytest.mark.parametrize("name", ["panda", "ur5"])
 def test_evaluator_unaligned_and_ragged_device_inputs(name):
     """The evaluator's TMA tile loads need 16-byte aligned joint vectors and full 32-configuration tiles; a device
