@@ -522,6 +522,46 @@ def run_product(args):
     idx = np.where(st_h == 1)[0][:: max(1, int((st_h == 1).sum()) // 512)][:512]
     oracle_ok = all(ch.objective(q_h[i], tgt_h) < TOL_F and np.all(q_h[i] >= lb) and np.all(q_h[i] <= ub) for i in idx)
 
+    # ---- the same passes in throughput mode, still device-timed with device-resident inputs (single GPU only): DT_STREAMS
+    # streams, each pass on SMs / E2E_SM_DIV blocks, so that several passes are co-resident.  This is the device-side
+    # twin of the e2e leg below (it explains why e2e beats the isolated-pass `value`); converged attempts are the
+    # kernel's own count (status == 1, which the gated loop above shows to equal the re-verified count).
+    dev_tp = None
+    if world == 1 and (tile or 1) == 1:
+        DT_STREAMS, DT_PASSES = 8, min(NP, 1024)
+        dt_blocks = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // E2E_SM_DIV)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(DT_STREAMS)]
+        bufs = [((torch.empty((R, n), dtype=torch.float64, device=dev), torch.empty((R,), dtype=torch.float64, device=dev),
+                  torch.empty((R,), dtype=torch.int32, device=dev), torch.empty((R,), dtype=torch.int32, device=dev)),
+                 torch.empty((obd.RECORD_HEAD + n,), dtype=torch.float64, device=dev)) for _ in range(DT_STREAMS)]
+        cnt_tp = torch.zeros(3, dtype=torch.int64, device=dev)
+        for k in range(DT_STREAMS):  # warm every stream
+            with torch.cuda.stream(streams[k]):
+                robot.ik_attempts(cfg, targets[k], x0, R, tile=tile, best=True, out=bufs[k][0], record=bufs[k][1], blocks=dt_blocks)
+        torch.cuda.synchronize()
+        flush.fill_(1)
+        t_a = torch.cuda.Event(enable_timing=True)
+        t_b = [torch.cuda.Event(enable_timing=True) for _ in range(DT_STREAMS)]
+        torch.cuda.synchronize()
+        t_a.record()
+        for st_ in streams:
+            st_.wait_event(t_a)
+        for s in range(DT_PASSES):
+            k = s % DT_STREAMS
+            with torch.cuda.stream(streams[k]):
+                robot.ik_attempts(cfg, targets[s], x0, R, tile=tile, best=True, counters=cnt_tp, out=bufs[k][0], record=bufs[k][1],
+                                  blocks=dt_blocks)
+        for k in range(DT_STREAMS):
+            t_b[k].record(streams[k])
+        torch.cuda.synchronize()
+        tp_ms = max(t_a.elapsed_time(e) for e in t_b)
+        conv_tp = int(cnt_tp[2])
+        dev_tp = {"value": conv_tp / (tp_ms * 1e-3), "unit": UNIT, "ms_per_pass": tp_ms / DT_PASSES, "passes": DT_PASSES,
+                  "streams": DT_STREAMS, "blocks_per_pass": dt_blocks, "evals_per_s": int(cnt_tp[1]) / (tp_ms * 1e-3),
+                  "note": "device-resident inputs and outputs, CUDA events from the first launch to the last stream's end; "
+                          "converged = status == 1 as counted by the kernel; L2 flushed once before the region"}
+        del bufs, streams
+
     # ---- e2e: the same pass through the public host-buffer API (H2D of target/x0, D2H of every record, per pass).
     # Two legs: (a) one blocking call per pass; (b) the headline: calls enqueued on two library streams with two sets
     # of pinned buffers (OPTIK_BATCH_ASYNC), so one pass's D2H overlaps the next pass's kernels -- every pass still
@@ -741,6 +781,7 @@ def run_product(args):
             "gpu_launches": (1 if world == 1 else (2 if px is not None else 3)) * NP,
             "exchange": (None if world == 1 else "peer-to-peer stores over NVLink (optik_gpu_exchange_push/_select)" if px is not None
                          else "ncclAllGather + optik_gpu_select_records"),
+            "device_throughput_mode": dev_tp,
             "roofline": roof,
             "roofline_solve": {"kernel": "solve_t1_kernel" if (tile or 1) == 1 else f"solve_kernel<{tile}>",
                                "bound": "fp64 issue / dependency latency (not HBM, not tensor)",
