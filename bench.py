@@ -694,7 +694,8 @@ def run_product(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:  # DRAM bytes of this exact launch shape from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_eval_traffic.json")))
+            tf_name = "r02_eval_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_eval_traffic.json")) else "r01b_eval_traffic.json"
+            tr = json.load(open(os.path.join(ROOT, "profiles", tf_name)))
             if tr["evals_per_launch"] == B:
                 traffic = tr["traffic_bytes_per_launch"]
         except Exception:
@@ -703,7 +704,7 @@ def run_product(args):
         roof = {"kernel": "eval_kernel (batched FK + 6xn body Jacobian + se3-log error + gradient, fp64 I/O)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "traffic_source": "profiles/r01b_eval_traffic.json (ncu dram bytes read+write per launch)",
+                "traffic": traffic, "traffic_source": f"profiles/{tf_name} (ncu dram bytes read+write per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": B * bytes_per_eval, "launch_ms": ms,
                 "evals_per_launch": B, "inputs": "4 Mi configurations x (56 B q + 64 B target) in, 464 B out each: > L2"}
         del rngq, tgB

@@ -11,4 +11,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 for w in step speed quality snake single; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"solve_t1|solve_kernel" -s 2 -c 2 -f -o gpurun_out/r02_prof_$w python tools/profile_t1.py $w > gpurun_out/prof_$w.log 2>&1; tail -1 gpurun_out/prof_$w.log
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:eval_kernel -s 2 -c 1 -f -o gpurun_out/r02_prof_eval python tools/profile_target.py eval > gpurun_out/prof_eval.log 2>&1; tail -1 gpurun_out/prof_eval.log
 ls -la gpurun_out

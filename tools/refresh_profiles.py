@@ -20,6 +20,23 @@ for w, t in titles.items():
                               f"ncu --set full --clock-control none (tools/gpu_round2.sh -> tools/profile_t1.py {w}), round 2: {t}"],
                              capture_output=True, text=True, check=True).stdout
         open(os.path.join(P, f"r02_{w}_kernels_ncu.txt"), "w").write(out)
+# evaluator: summary + DRAM traffic of the roofline launch (bench.py reads r02_eval_traffic.json)
+rep = os.path.join(G, "r02_prof_eval.ncu-rep")
+if os.path.exists(rep):
+    import json
+    out = subprocess.run([py, os.path.join(ROOT, "tools", "ncu_summary.py"), rep,
+                          "ncu --set full --clock-control none (tools/gpu_round2.sh -> tools/profile_target.py eval), round 2: eval_kernel<7,true,128>, "
+                          "4 Mi Panda configurations (the bench.py roofline launch)"], capture_output=True, text=True, check=True).stdout
+    open(os.path.join(P, "r02_eval_kernel_ncu.txt"), "w").write(out)
+    def val(key):
+        m = re.search(re.escape(key) + r" \[(\w+)\] = ([0-9.]+)", out)
+        return float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(1)]
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    B = 1 << 22
+    json.dump({"kernel": "eval_kernel<7,true,128>", "evals_per_launch": B, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+               "traffic_bytes_per_launch": int(rd + wr), "algorithmic_bytes_per_launch": B * 8 * (8 * 7 + 17),
+               "source": "ncu --set full --clock-control none, profiles/r02_eval_kernel_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum), "
+                         "same launch shape as bench.py's roofline pass"}, open(os.path.join(P, "r02_eval_traffic.json"), "w"), indent=1)
 rep = os.path.join(G, "r02_prof_step.ncu-rep")
 if os.path.exists(rep):
     out = subprocess.run([py, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, os.path.join(ROOT, "optik_b200", "csrc", "solve_t1_kernel.cu")],
