@@ -32,12 +32,14 @@ import numpy as np  # noqa: E402
 SEEDS_PER_GPU = 65536
 MIN_TIMED_SECONDS = 1.0
 CPU_BASELINE_PASSES = 32  # cpu_baseline sample: 32 full passes (2 Mi attempts, ~20 CPU-seconds on 16 cores)
-E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "8"))  # host-buffer calls in flight on one GPU
-# e2e throughput mode: every pass is launched on a FRACTION of the machine (opts.blocks = SMs / E2E_SM_DIV, one block per
-# SM on every other SM's worth of slots) so that several passes are co-resident and one pass's straggler tail runs under
-# the next passes' bulk (measured on B200, tools/exp_e2e.py: full-machine launches 0.208 ms/pass at any depth, half of the
-# SMs' blocks with 8 passes in flight 0.150 ms/pass; the device-timed `value` stays the isolated full-machine pass)
-E2E_SM_DIV = int(os.environ.get("OPTIK_BENCH_E2E_SM_DIV", "2"))
+E2E_DEPTH_SINGLE = int(os.environ.get("OPTIK_BENCH_E2E_DEPTH", "10"))  # host-buffer calls in flight on one GPU
+# e2e throughput mode: every pass is launched on a FRACTION of the machine (opts.blocks = SMs / E2E_SM_DIV: a third of the
+# SM count = a sixth of the resident block slots) so that several passes are co-resident and one pass's straggler tail runs
+# under the next passes' bulk (measured on B200, tools/exp_e2e.py: full-machine launches 0.208 ms/pass at any depth, 74
+# blocks with 8 passes in flight 0.150, 49 blocks with 10 in flight 0.143, 29 blocks with 16 in flight 0.137 ms/pass; the
+# device-timed `value` stays the isolated full-machine pass).  Several GPUs: half of the SM count, 8 passes in flight.
+E2E_SM_DIV = int(os.environ.get("OPTIK_BENCH_E2E_SM_DIV", "3"))
+E2E_SM_DIV_MULTI = 2
 PT_DEPTH = 3  # per_target e2e: host-buffer batch calls in flight
 E2E_DEPTH_MULTI = 8  # host-buffer steps in flight per rank when a collective sits inside the step (N > 1)
 ROBOT = "panda"
@@ -528,7 +530,7 @@ def run_product(args):
     # kernel's own count (status == 1, which the gated loop above shows to equal the re-verified count).
     dev_tp = None
     if world == 1 and (tile or 1) == 1:
-        DT_STREAMS, DT_PASSES = 8, min(NP, 1024)
+        DT_STREAMS, DT_PASSES = E2E_DEPTH_SINGLE, min(NP, 1024)
         dt_blocks = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // E2E_SM_DIV)
         streams = [torch.cuda.Stream(device=dev) for _ in range(DT_STREAMS)]
         bufs = [((torch.empty((R, n), dtype=torch.float64, device=dev), torch.empty((R,), dtype=torch.float64, device=dev),
@@ -605,7 +607,8 @@ def run_product(args):
     e2e_conv = 0
     host_submit_s = 0.0
     D = E2E_DEPTH_SINGLE if world == 1 else E2E_DEPTH_MULTI
-    e2e_blocks = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // E2E_SM_DIV) if (tile or 1) == 1 else 0
+    e2e_blocks = (max(1, torch.cuda.get_device_properties(dev).multi_processor_count // (E2E_SM_DIV if world == 1 else E2E_SM_DIV_MULTI))
+                  if (tile or 1) == 1 else 0)
     if world == 1 or px is not None:
         while len(sets) < D:
             sets.append(((ob.pinned_empty((R, n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
