@@ -710,6 +710,32 @@ def run_product(args):
                 "traffic": traffic, "traffic_source": f"profiles/{tf_name} (ncu dram bytes read+write per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": B * bytes_per_eval, "launch_ms": ms,
                 "evals_per_launch": B, "inputs": "4 Mi configurations x (56 B q + 64 B target) in, 464 B out each: > L2"}
+        # the reference's CPU path for the same work, timed beside it (oracle restatement of one objective callback with a
+        # gradient request per configuration: FK once, Jacobian, Jlog6, log twice; all host cores and one core)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            chE = O.Chain(robot.chain())
+            Bc = 1 << 20
+            qh, th_ = rngq[:Bc].cpu().numpy(), tgB[:Bc].cpu().numpy()
+            cores = os.cpu_count() or 1
+            outc = O.eval_batch_threaded(chE, qh[:4096], th_[:4096], 1)
+            gq = robot.eval_batch(rngq[:4096], tgB[:4096])
+            ev_ok = bool(np.abs(gq["f"].cpu().numpy() - outc["f"]).max() <= 1e-12 and
+                         np.abs(gq["jac"].cpu().numpy().reshape(4096, n, 6) - outc["jac"]).max() <= 1e-12)
+            outc = O.eval_batch_threaded(chE, qh, th_, cores)  # first touch of the output pages
+            t0 = time.perf_counter()
+            O.eval_batch_threaded(chE, qh, th_, cores, out=outc)
+            t_all = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            O.eval_batch_threaded(chE, qh[:Bc // 8], th_[:Bc // 8], 1, out={k: v[:Bc // 8] for k, v in outc.items()})
+            t_one = time.perf_counter() - t0
+            roof["cpu_baseline"] = {"value": Bc / t_all, "unit": "configurations/s", "cores": cores, "kind": "port",
+                                    "value_1_core": (Bc // 8) / t_one, "gpu_value": B / (ms * 1e-3),
+                                    "gpu_matches_oracle_1e-12": ev_ok,
+                                    "sample": f"{Bc} of the launch's Panda configurations, oracle/optik_oracle.c "
+                                              "oracle_eval_batch_threaded (the work of one reference objective callback with "
+                                              "gradient per configuration, lib.rs:305-337), fp64, gcc -O3; output pages touched first"}
+            del outc
         del rngq, tgB
         fp64_peak = float(ob.load_library().optik_measure_fp64_peak(local_rank, 2.0))
 

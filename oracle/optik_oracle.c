@@ -353,3 +353,65 @@ double oracle_uniform(uint64_t u, double lb, double ub) {
 void oracle_restart_seed(uint64_t restart, const double* lb, const double* ub, int n, double* q) {
   for (int i = 0; i < n; i++) q[i] = oracle_uniform(oracle_rng_u64(42, restart, (uint32_t)i), lb[i], ub[i]);
 }
+
+/* ------------------------------------------------------------------ evaluator batch (bench.py: the CPU number beside the
+ * evaluator kernel's roofline).  Per configuration the work of ONE objective callback of the reference with a gradient
+ * request (lib.rs:305-337): forward_kinematics_mut once, objective_grad (joint_jacobian + se3::right_jacobian + se3::log +
+ * weighting + the 6 x n product, objective.rs:60-110), then objective (se3::log again, objective.rs:40-57); plus the
+ * outputs the CUDA evaluator writes (ee pose, the body Jacobian itself).  `threads` pthread workers over contiguous
+ * ranges, no allocation inside the loop. */
+#include <pthread.h>
+typedef struct {
+  const double* chain; int njoints, n;
+  const double *q, *targets;
+  double *ee, *jac, *f, *grad;
+  uint64_t begin, end;
+} evjob_t;
+
+static void* eval_worker(void* arg) {
+  evjob_t* W = (evjob_t*)arg;
+  const double one[3] = {1.0, 1.0, 1.0};
+  double* tf = (double*)malloc(sizeof(double) * 8 * (size_t)W->njoints);
+  for (uint64_t i = W->begin; i < W->end; i++) {
+    const double* q = W->q + i * (uint64_t)W->n;
+    const double* tg = W->targets + 8 * i;
+    double* ee = W->ee + 8 * i;
+    double* J = W->jac + i * 6ull * (uint64_t)W->n;
+    double X[8], U[36], e[6], e2[6];
+    oracle_fk(W->chain, W->njoints, q, NULL, tf, ee);
+    pose_inv_mul(tg, ee, X);
+    oracle_joint_jacobian(W->chain, W->njoints, tf, ee, J);
+    oracle_se3_right_jacobian(X, U);
+    oracle_se3_log(X, e);
+    apply_weighting(e, tg, one, one); /* squared weights, objective.rs:102-104 */
+    for (int c = 0; c < W->n; c++) {
+      double s = 0;
+      for (int r = 0; r < 6; r++) {
+        double jt = 0;
+        for (int k = 0; k < 6; k++) jt += U[6 * k + r] * J[6 * c + k];
+        s += 2.0 * e[r] * jt;
+      }
+      W->grad[i * (uint64_t)W->n + c] = s;
+    }
+    oracle_se3_log(X, e2); /* objective(): the log once more */
+    apply_weighting(e2, tg, one, one);
+    W->f[i] = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2] + e2[3] * e2[3] + e2[4] * e2[4] + e2[5] * e2[5];
+  }
+  free(tf);
+  return NULL;
+}
+
+int oracle_eval_batch_threaded(const double* chain, int njoints, const double* q, const double* targets, uint64_t B,
+                               int threads, double* ee, double* jac, double* f, double* grad) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  const int n = oracle_num_positions(chain, njoints);
+  pthread_t th[256];
+  evjob_t jobs[256];
+  for (int t = 0; t < threads; t++) {
+    jobs[t] = (evjob_t){chain, njoints, n, q, targets, ee, jac, f, grad, B * (uint64_t)t / threads, B * (uint64_t)(t + 1) / threads};
+    if (pthread_create(&th[t], NULL, eval_worker, &jobs[t]) != 0) return -1;
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  return 0;
+}

@@ -268,3 +268,22 @@ def ref_batch_threaded(chain, targets, x0, restarts, mode="speed", threads=1, pa
             2 if mode == "speed" else 1, int(threads), _p(q), _p(f), found.ctypes.data_as(C.POINTER(C.c_int)))
     assert rc == 0
     return q, f, found.astype(bool)
+
+
+def eval_batch_threaded(chain, q, targets, threads=1, out=None):
+    """Reference-style evaluator over a batch (FK + body Jacobian + objective + gradient per configuration, the
+    reference's own call sequence) on `threads` pthread workers: bench.py's CPU number beside the evaluator kernel.
+    Returns dict(ee (B,8), jac (B,n,6) = column-major 6 x n per configuration, f (B,), grad (B,n))."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    targets = np.ascontiguousarray(targets, dtype=np.float64)
+    B, n = q.shape
+    assert n == chain.n and targets.shape == (B, 8)
+    if out is None:  # (pass the dict of a previous call to time the arithmetic without first-touch page faults)
+        out = dict(ee=np.zeros((B, 8)), jac=np.zeros((B, n, 6)), f=np.zeros(B), grad=np.zeros((B, n)))
+    ee, jac, f, grad = out["ee"], out["jac"], out["f"], out["grad"]
+    fn = lib().oracle_eval_batch_threaded
+    fn.argtypes = [dp, C.c_int, dp, dp, C.c_uint64, C.c_int, dp, dp, dp, dp]
+    fn.restype = C.c_int
+    rc = fn(_p(chain.arr), chain.njoints, _p(q), _p(targets), B, int(threads), _p(ee), _p(jac), _p(f), _p(grad))
+    assert rc == 0, rc
+    return out

@@ -134,3 +134,25 @@ def test_restart_seeds_uniform_in_limits(ur3e):
     assert np.abs(qs.mean(0)).max() < 0.2
     assert np.abs(qs.std(0) - (ur3e.ub - ur3e.lb) / np.sqrt(12)).max() < 0.1
     assert np.array_equal(ur3e.restart_seed(7), ur3e.restart_seed(7))
+
+
+def test_batch_evaluator_equals_single_calls():
+    """oracle_eval_batch_threaded (bench.py's CPU number beside the evaluator kernel) returns exactly what the
+    golden-pinned single-configuration functions return, for any thread count."""
+    from oracle import urdf_chain
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    ch = O.Chain.from_urdf(open(os.path.join(here, "..", "optik_b200", "data", "ur3e.urdf")).read(), "ur_base_link", "ur_ee_link")
+    rng = np.random.default_rng(9)
+    B = 257
+    q = rng.uniform(ch.lb, ch.ub, size=(B, ch.n))
+    tg = np.stack([ch.fk(rng.uniform(ch.lb, ch.ub))[1] for _ in range(B)])
+    a = O.eval_batch_threaded(ch, q, tg, 1)
+    b = O.eval_batch_threaded(ch, q, tg, 3)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    for i in range(0, B, 16):
+        assert a["f"][i] == ch.objective(q[i], tg[i])
+        assert np.array_equal(a["grad"][i], ch.objective_grad(q[i], tg[i]))
+        assert np.array_equal(a["jac"][i].T, ch.joint_jacobian(q[i]))
+        assert np.array_equal(a["ee"][i], ch.fk(q[i])[1])
