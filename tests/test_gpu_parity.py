@@ -868,6 +868,43 @@ def test_solve_against_slsqp_standin(name, R):
           f"{max(own_start) if own_start else float('nan'):.2e} rad")
 
 
+def test_co_resident_passes_on_several_streams_equal_sequential_passes():
+    """bench.py's throughput mode: per-attempt passes enqueued on several streams, each on a fraction of the machine
+    (opts.blocks), are co-resident on the GPU and share the robot's seed table and scratch pool.  Every pass must give
+    exactly the records of the same pass run alone (device path with torch streams, and the asynchronous host path)."""
+    import torch
+    r, ch = robot_and_chain("panda")
+    rng = np.random.default_rng(21)
+    R, NPASS, NSTREAM = 8192, 12, 4
+    tg = torch.from_numpy(targets_for(ch, rng, NPASS)).cuda()
+    x0 = torch.from_numpy(0.5 * (ch.lb + ch.ub)).cuda()
+    cfg = ob.SolverConfig(solution_mode="quality", max_time=0.0, max_restarts=R)
+    alone = [tuple(t.clone() for t in r.ik_attempts(cfg, tg[i], x0, R, best=True)) for i in range(NPASS)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(NSTREAM)]
+    outs = []
+    for i in range(NPASS):
+        with torch.cuda.stream(streams[i % NSTREAM]):
+            outs.append(r.ik_attempts(cfg, tg[i], x0, R, best=True, blocks=37))
+    torch.cuda.synchronize()
+    for i in range(NPASS):
+        for a, b in zip(alone[i], outs[i]):
+            assert torch.equal(a, b), i
+    # host path: pinned buffers, OPTIK_BATCH_ASYNC, one library stream per call in flight
+    tg_h, x0_h = ob.pinned_empty((NPASS, 8)), ob.pinned_empty(ch.n)
+    tg_h[:] = tg.cpu().numpy()
+    x0_h[:] = x0.cpu().numpy()
+    sets = [((ob.pinned_empty((R, ch.n)), ob.pinned_empty(R), ob.pinned_empty(R, np.int32), ob.pinned_empty(R, np.int32)),
+             ob.pinned_empty(ob.RECORD_HEAD + ch.n), ob.Stream(r)) for _ in range(NPASS)]
+    for i in range(NPASS):
+        r.ik_attempts(cfg, tg_h[i], x0_h, R, best=True, out=sets[i][0], record=sets[i][1], stream=sets[i][2], wait=False, blocks=37)
+    for i in range(NPASS):
+        sets[i][2].synchronize()
+        for a, b in zip(alone[i][:4], sets[i][0]):
+            assert np.array_equal(a.cpu().numpy(), b), i
+        assert np.array_equal(alone[i][4].cpu().numpy(), sets[i][1]), i
+
+
 def test_peer_exchange_kernels_single_gpu():
     """optik_gpu_exchange_push / _select (the NVLink best-pick exchange) with four simulated ranks on one GPU: each
     'rank' owns a buffer, every push lands in every buffer, every select returns the record the torch specification of
