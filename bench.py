@@ -737,6 +737,12 @@ def run_product(args):
                                               "gradient per configuration, lib.rs:305-337), fp64, gcc -O3; output pages touched first"}
             del outc
         del rngq, tgB
+        # what HBM gives a kernel with this read/write mix and no arithmetic at all (120 B in, 464 B out per item -> 8 and
+        # 29 sixteen-byte units, fully coalesced): the practical ceiling beside the copy figure
+        mix = float(ob.load_library().optik_measure_hbm_mix(local_rank, B, 8, 29, 5))
+        roof["mix_ceiling"] = {"achieved": mix, "unit": "GB/s", "frac_of_peak": mix / peak, "eval_frac_of_ceiling": achieved / mix if mix > 0 else None,
+                               "what": "pure streaming kernel, 128 B read + 464 B written per item, same item count, coalesced, "
+                                       "best of 5 launches (optik_measure_hbm_mix)"}
         fp64_peak = float(ob.load_library().optik_measure_fp64_peak(local_rank, 2.0))
 
     # ---- the other BASELINE configs and the per-target headline (every rank runs its own copy; rank 0 reports)

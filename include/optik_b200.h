@@ -276,6 +276,9 @@ void optik_gpu_stream_destroy(void* stream);
 /* Measurement helper (bench.py `roofline_solve`): fp64 FMA throughput of `device` in TFLOP/s, sustained over about
  * `seconds` of launches of a register-only DFMA kernel (8 independent chains per thread); < 0 on error. */
 double optik_measure_fp64_peak(int device, double seconds);
+/* Measurement only: GB/s of a pure streaming kernel that reads rd_units and writes wr_units 16-byte units per item, fully
+ * coalesced, over `items` items (best of `reps` launches): what HBM delivers at the evaluator's read/write mix. */
+double optik_measure_hbm_mix(int device, unsigned long long items, int rd_units, int wr_units, int reps);
 
 /* Pinned host allocations for fast, truly asynchronous host<->device copies. */
 void* optik_host_alloc(uint64_t bytes);

@@ -106,6 +106,7 @@ def load_library():
         "optik_gpu_stream_sync": (C.c_int, [vp]),
         "optik_gpu_stream_destroy": (None, [vp]),
         "optik_measure_fp64_peak": (C.c_double, [C.c_int, C.c_double]),
+        "optik_measure_hbm_mix": (C.c_double, [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
         "optik_host_alloc": (vp, [C.c_uint64]),
         "optik_host_free": (None, [vp]),
     }
