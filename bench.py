@@ -16,6 +16,12 @@ re-checked by the golden-pinned CPU oracle), device time (CUDA events, max over 
 SURVEY section 8(d) -- IK problems solved per second -- is the `per_target` block (Panda, 1 Mi independent reachable
 targets, Speed, <= 32 restarts, through optik_gpu_ik_batch) and `configs` carries BASELINE configs 1, 3, 4 (and 5 on
 N > 1 GPUs), each next to the CPU port on the same workload (N = 1 only).
+
+`value` times every pass ALONE on the whole GPU.  `e2e` is the same pass through the host-buffer API in throughput mode
+(asynchronous calls, several in flight, each on a fraction of the machine: E2E_* below) and `device_throughput_mode` its
+device-only twin.  `roofline` = the evaluator kernel against the measured HBM copy peak, with the measured ceiling of a
+pure streaming kernel at the same read/write mix (`mix_ceiling`) and the oracle's CPU evaluator (`cpu_baseline`) beside
+it; `roofline_solve` = the solve kernel against an fp64 FMA peak measured in the same run.
 """
 import argparse
 import json
