@@ -218,3 +218,25 @@ def test_batch_opts_flags_match_the_header():
     # a clamped-seed flag never changes the success classification (lib.rs:376-379 on the status code)
     cfg = ob.SolverConfig(max_time=0.0, max_restarts=1)
     assert list(cfg.is_success(np.array([1, 1 | 0x100, 5 | 0x100, 2]))) == [True, True, False, False]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path: oracle port on the host cores) prints ONE JSON line on stdout
+    with the contract's keys, never touches a GPU and never maps the product library."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout[:2000]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["gpu_launches"] == 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
