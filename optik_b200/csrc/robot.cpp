@@ -138,7 +138,10 @@ struct DevBuf {  // grow-only device scratch
 // One in-flight Robot::ik() call: its own stream, persistent device scratch (control words + one wave of candidate
 // records) and a mapped pinned host block the kernel reads its inputs from and writes its result + completion flag to.
 constexpr int IK_SLOTS = 8;
-constexpr uint64_t IK_WAVE = 256;  // restarts per launch of a single-target call
+#ifndef OPTIK_IK_WAVE
+#define OPTIK_IK_WAVE 256
+#endif
+constexpr uint64_t IK_WAVE = OPTIK_IK_WAVE;  // restarts per launch of a single-target call
 struct IkSlot {
   std::atomic<bool> busy{false};
   bool ready = false;
