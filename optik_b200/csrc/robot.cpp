@@ -431,11 +431,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const size_t off_ev = ((direct && d_evals) || dyn) ? 0 : carve(njobs * sizeof(int));
   const bool use_found = speed && C > 1 && !per_attempt_records;
   const size_t off_found = use_found ? carve(T * sizeof(unsigned long long)) : 0;
-  // dynamic chains: [queue | ticket head | ticket tail (one 128-byte line each) | next[T] | ticket ring] zeroed
-  // together, the per-target found / record words [T] set to ~0
-  unsigned help_cap = 1;
-  if (dyn) while (help_cap < 4u * (unsigned)plan0.resident_tiles) help_cap <<= 1;
-  const size_t dyn_zero = 384 + T * sizeof(unsigned) + (size_t)help_cap * sizeof(unsigned);
+  // dynamic chains: [queue (one 128-byte line) | next[T]] zeroed together, the per-target found / record words [T] set to ~0
+  const size_t dyn_zero = 128 + T * sizeof(unsigned);
   const size_t off_zero = carve(dyn ? dyn_zero : 16);  // static: [queue (8 B) | fused_done (4 B)]
   const bool fused = tile == 1 && per_attempt_records && T == 1 && d_best_record != nullptr;  // selection inside the solve launch
   const size_t off_fpart = fused ? carve((size_t)plan.blocks * 24) : 0;
@@ -486,10 +483,7 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   P.found = nullptr;
   if (dyn) {
     P.sched = 1;
-    P.dyn_ctl = (unsigned long long*)(sc + off_zero + 128);
-    P.dyn_next = (unsigned*)(sc + off_zero + 384);
-    P.help_slots = P.dyn_next + T;
-    P.help_mask = help_cap - 1;
+    P.dyn_next = (unsigned*)(sc + off_zero + 128);
     P.dyn_word = (unsigned long long*)(sc + off_dfound);
     const uint64_t lanes = (uint64_t)plan0.resident_tiles;
     P.dyn_k0 = T >= lanes ? 0u : (unsigned)((lanes + T - 1) / T - 1);

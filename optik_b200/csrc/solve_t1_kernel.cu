@@ -22,13 +22,12 @@
 //   sched 2  per-attempt records: job = one restart of the one target (optik_gpu_ik_attempts, BASELINE config 2)
 //   sched 0  static jobs (target, chunk): chunk c runs restarts r_begin+c, +C, ... in order (Quality batches, small
 //            Speed batches with the `found` early exit)
-//   sched 1  dynamic Speed chains: a lane that takes a target claims its restarts one by one (atomicAdd on next[t]) until
-//            one converges; once every target has been taken, lanes whose chain ended pop HELP TICKETS that failing
-//            chains push and claim restarts of the same target in parallel.  A claimed index always runs unless a LOWER
-//            index has already converged (found[t], lib.rs:308, 382-384), so the per-target answer is the lowest-index
-//            converged restart (lib.rs:409-412 with one thread) regardless of timing; no host round trip, no tail of
-//            unlucky targets.  Tickets are hints (a lost one costs parallelism, never correctness); a warp leaves when
-//            every target has been taken, none of its lanes runs a chain and no ticket shows up for a few polls.
+//   sched 1  dynamic Speed chains: a lane that takes a target claims its restarts one by one until one converges; once
+//            every target has been taken, lanes left without work join the chains that still run in THEIR warp and claim
+//            restarts of the same targets in parallel.  A claimed index always runs unless a LOWER index has already
+//            converged (found[t], lib.rs:308, 382-384), so the per-target answer is the lowest-index converged restart
+//            (lib.rs:409-412 with one thread) regardless of timing; no host round trip, no tail of unlucky targets.  A
+//            warp leaves when every target has been taken and none of its lanes runs a chain.
 #include <cuda_runtime.h>
 
 #include "ik_math.cuh"
@@ -105,14 +104,6 @@ __global__ void chacha8_kat_kernel(const uint32_t* __restrict__ key_g, unsigned 
   uint64_t u[8];
   chacha8_block(key, 0, stream, u);
   for (int k = 0; k < 8; k++) { out16[2 * k] = (uint32_t)u[k]; out16[2 * k + 1] = (uint32_t)(u[k] >> 32); }
-}
-
-// ---- help-ticket ring of the dynamic scheduler: head = dyn_ctl[0], tail = dyn_ctl[16] (separate 128-byte lines).
-// Overflow overwrites unconsumed tickets and a consumer may read a slot twice (second time 0): both only lose hints.
-constexpr int CTL_TAIL = 16;
-DEV void help_push(const SolveParams& P, unsigned t) {
-  const unsigned long long s = atomicAdd(P.dyn_ctl + CTL_TAIL, 1ull);
-  atomicExch(P.help_slots + (unsigned)(s & P.help_mask), t + 1u);
 }
 
 // ---- per-target word of the dynamic scheduler: high half = lowest converged relative restart index so far (DYN_NONE:
@@ -213,10 +204,6 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
   bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
   unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
-  int idle_polls = 0;   // warp-uniform: consecutive transition passes without any chain or ticket in this warp
-  unsigned n_idle = 0;  // warp-uniform: lanes left without work by the last transition pass
-  unsigned n_help = 1;  // warp-uniform: tickets a failing chain pushes
-  unsigned help_next = 0, help_gap = 1;  // warp-uniform: pass of the next look for help work, current back-off
   unsigned long long pool_next = 0, pool_end = 0;  // warp-uniform: this warp's claimed range of the job queue
   double fc = 0.0, rc[6] = {0, 0, 0, 0, 0, 0}, lambda = P.lambda0, best_score = 0.0;
   int have_cur = 0, slow = 0, evals = 0, job_evals = 0, cur = 0;
@@ -354,45 +341,10 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
             want = __ballot_sync(FULLMASK, idle && !got);
           }
         }
-        // (C) help tickets, one pop of k tickets per warp
-        // (polled with a back-off of 2, 4, 8 passes while lanes of this warp run: the poll is two global loads)
-        const bool look = want && wfd && !late && (pass >= help_next || !__any_sync(FULLMASK, running));
-        const unsigned want0 = want;
-        if (look) {
-          const int leader = __ffs(want) - 1;
-          unsigned long long h = 0;
-          unsigned k = 0;
-          if (lane == leader) {
-            h = *((volatile unsigned long long*)(P.dyn_ctl + 0));
-            const unsigned long long tl = *((volatile unsigned long long*)(P.dyn_ctl + CTL_TAIL));
-            if (tl > h) {
-              k = (unsigned)min((unsigned long long)__popc(want), tl - h);
-              if (atomicCAS(P.dyn_ctl + 0, h, h + k) != h) k = 0;  // lost the race; next pass
-            }
-          }
-          h = __shfl_sync(FULLMASK, h, leader);
-          k = __shfl_sync(FULLMASK, k, leader);
-          const unsigned rank = __popc(want & ((1u << lane) - 1u));
-          if (idle && !got && rank < k) {
-            const unsigned v = atomicExch(P.help_slots + (unsigned)((h + rank) & P.help_mask), 0u);
-            if (v && dyn_found_of(P, v - 1u) == DYN_NONE) {
-              const unsigned long long rel = dyn_base + atomicAdd(P.dyn_next + (v - 1u), 1u);
-              if (rel < nrest) { tgt_id = v - 1u; r_idx = P.r_begin + rel; got = true; job_open = true; excl = false; no_help = false; }
-            }
-          }
-        }
-        // leave when nothing is left to do here: all targets taken, no chain in this warp, no ticket for a few polls
-        n_idle = __popc(__ballot_sync(FULLMASK, idle && !got));
-        if (look) {  // nobody got a ticket: back off
-          help_gap = (n_idle == __popc(want0)) ? min(help_gap * 2u, 8u) : 1u;
-          help_next = pass + help_gap;
-        }
-        n_help = n_idle >= 16 ? 2u : 1u;
-        if (wfd) {
-          if (__any_sync(FULLMASK, running || got)) idle_polls = 0;
-          else if (late || ++idle_polls > 6) { if (idle) done = true; }
-          else __nanosleep(1000);
-        }
+        // leave when nothing is left to do here: every target has been taken and no lane of this warp runs a chain.
+        // (Help across warps -- tickets that failing chains pushed and other warps popped -- was measured to add nothing
+        // once the speculation above existed, and was removed: the warps that could have helped are gone by then.)
+        if (wfd && !__any_sync(FULLMASK, running || got)) { if (idle) done = true; }
       }
       if (got) {  // restart 0 = the caller's seed, i >= 1 = ChaCha8 stream i (lib.rs:360-370)
         if (r_idx == 0) {  // (loads issued eight at a time: one memory latency per group, not per joint)
@@ -584,29 +536,16 @@ T1_HOT_UNROLL
             if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
           }
           if (success) job_open = false;  // first success ends the chain (lib.rs:381-387, 411)
-          else if (wfd && status != OPTIK_ST_SKIPPED && my_next < nrest) {
-            // every target has been taken: a failing chain invites helpers, which claim this target's next restarts in
-            // parallel (two when half of this warp's lanes were left without work by the last transition pass; pushing
-            // as many tickets as there are idle lanes was measured slower: stale tickets flood the ring).  From here on
-            // the target is shared: restart counter, found[] and the record lock live in memory.
-            // (the chain's own next restart is my_next: it goes on with it, the helpers claim from my_next + 1)
-            pre_rel = my_next; pre_ok = true;
-            atomicExch(P.dyn_next + tgt_id, my_next + 1u);
-            __threadfence();
-            for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
-            excl = false;
-          }
+          // (a failing chain stays exclusive: its counter is published when an idle lane of its warp joins it)
         } else {
           // shared target.  A failed attempt claims the chain's next restart and reads found[t] right here -- two
-          // independent requests in flight together with the tickets, consumed by the next transition pass.  A record
+          // independent requests in flight together, consumed by the next transition pass.  A record
           // is written under the target's word: one CAS takes the record and publishes the index (only a new lowest
           // index gets it; a higher one sees that and leaves), the row is written, fenced and the word released.
           if (!success && status != OPTIK_ST_SKIPPED) {
             const unsigned fnow = dyn_found_of(P, tgt_id);
             pre_rel = dyn_base + atomicAdd(P.dyn_next + tgt_id, 1u);
             pre_ok = fnow == DYN_NONE && pre_rel < nrest;
-            if (wfd)
-              for (unsigned k = 0; k < n_help; k++) help_push(P, (unsigned)tgt_id);
           }
           if (success || (rel == 0u && status != OPTIK_ST_SKIPPED)) {
             const unsigned pub = success ? rel : DYN_NONE;  // a failure record leaves found[t] empty

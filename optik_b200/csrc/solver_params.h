@@ -83,9 +83,6 @@ struct SolveParams {
   unsigned* dyn_next;                 // [T] next relative restart index to claim            (zeroed)
   unsigned long long* dyn_word;       // [T] high half: lowest converged relative restart index so far, low half: 1 while
                                       //     a writer holds the target's record                  (all ones)
-  unsigned long long* dyn_ctl;        // [0] ticket head [1] ticket tail [2] live chains     (zeroed)
-  unsigned* help_slots;               // [help_mask + 1] ticket ring, value = target + 1     (zeroed)
-  unsigned help_mask;
   // thread-per-seed kernel, sched = 2: selection fused into the solve launch (last block done).  fused_record = the
   // packed candidate record [8 + n]; partials are per block; fused_done is zeroed by the host.
   double* fused_record;
