@@ -310,9 +310,13 @@ int choose_tile(const optik_robot* r, uint32_t want, bool batch) {
 }
 // thread-per-seed kernel: rows = 2 keeps the trial columns in shared memory (2 blocks/SM), rows = 1 in local memory
 // (3 blocks/SM).  opts.variant forces one; the default is the measured better one.
-int t1_rows(const optik_robot* r, const optik_gpu_batch_opts* o, double attempts) {
+int t1_rows(const optik_robot* r, const optik_gpu_batch_opts* o, double attempts, bool speed_chains) {
   if (r->occ_t1[1] <= 0) return 1;  // long chains: two column rows per thread do not fit
   if (o && (o->variant == 1 || o->variant == 2)) return (int)o->variant;
+  // Speed batches of 7-joint arms: the one-row instance keeps its trial columns (6n doubles) in registers and spills
+  // from n = 7 on; with the divergence of Speed chains the two-row layout is then 3-6 % faster at every batch size
+  // (Panda 1 Mi targets 6.04 -> 5.83 ms; UR5, n = 6, is 4 % faster with one row; Quality batches 5 % faster with one row)
+  if (speed_chains && r->n >= 7) return 2;
   // three blocks per SM win once every lane runs several attempts (throughput); with about one attempt per lane the
   // launch is a latency chain and two blocks per SM with the trial columns in shared memory are faster
   const double lanes1 = (double)r->sm_count * (r->occ_t1[0] > 0 ? r->occ_t1[0] : 3) * (double)optik_solve_t1_threads(r->n, 1);
@@ -391,7 +395,8 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   const int tile = choose_tile(r, o ? o->tile : 0, true);
   if (!tile) return fail(OPTIK_ERR_INVALID, "opts.tile must be 1 (chains whose rows fit shared memory), 8, 16 or 32 and >= num_positions");
   const bool speed = cfg->solution_mode == OPTIK_MODE_SPEED;
-  const int rows = t1_rows(r, o, per_attempt_records ? (double)R : (speed ? 2.0 * (double)T : (double)T * (double)(R < 4096 ? R : 4096)));
+  const int rows = t1_rows(r, o, per_attempt_records ? (double)R : (speed ? 2.0 * (double)T : (double)T * (double)(R < 4096 ? R : 4096)),
+                           speed && !per_attempt_records);
   SolveParams P{};
   fill_common(r, cfg, o ? o->ee_offset : nullptr, o ? o->max_evals : 0, P);
   P.targets = d_targets; P.x0 = d_x0; P.T = T; P.r_begin = r_begin; P.r_end = r_begin + R;
