@@ -18,7 +18,7 @@
 // instructions; the in-kernel draw remains as the fallback for restart indices beyond the table.
 // Scheduling (lib.rs:297-301, 381-387, 393-413): a flattened state machine, every lane runs ONE uniform loop body
 // (evaluate -> stop tests -> step) and takes its next attempt when one ends.  The transition code is entered by the
-// whole warp (converged) whenever some lane needs work, so that queue fetches and ticket pops are warp-aggregated:
+// whole warp (converged) whenever some lane needs work, so that queue fetches are warp-aggregated:
 //   sched 2  per-attempt records: job = one restart of the one target (optik_gpu_ik_attempts, BASELINE config 2)
 //   sched 0  static jobs (target, chunk): chunk c runs restarts r_begin+c, +C, ... in order (Quality batches, small
 //            Speed batches with the `found` early exit)
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
   bool pre_ok = false;  // dynamic, shared target: pre_rel is a claimed restart index that may run
   unsigned long long pre_rel = 0;
   bool no_help = false; // dynamic: my chain cannot use helpers any more (no restart left / a restart of the target converged)
-  bool excl = false;    // dynamic: no other lane works on my target (no ticket pushed yet) -> no atomics, no lock
+  bool excl = false;    // dynamic: no other lane works on my target (nobody joined it yet) -> no atomics, no record word
   unsigned my_next = 0; // dynamic, exclusive chain: the next relative restart index of my target
   bool wfd = false;     // warp-uniform: every target of a dynamic launch has been taken
   unsigned long long pool_next = 0, pool_end = 0;  // warp-uniform: this warp's claimed range of the job queue
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(TB, (ROWS == 1 ? 3 : 2) * (128 / TB)) solve_t1
   for (;;) {
     pass++;
     // ---------------- transitions: lanes without an attempt take the next one.  Entered by the WHOLE warp (converged)
-    // whenever some lane needs work, so that queue fetches and ticket pops are one atomic per warp.
+    // whenever some lane needs work, so that queue fetches are one atomic per warp.
     const unsigned need = __ballot_sync(FULLMASK, !running && !done);
     if (need) {
       const bool idle = !running && !done;
