@@ -404,10 +404,12 @@ int solve_device(const optik_robot* r, const optik_solver_config* cfg, const opt
   P.counters = (unsigned long long*)d_counters;
   const int n = r->n;
   Plan plan0 = make_plan(r, tile, rows, o ? o->blocks : 0, ~0ull);
-  // ---- scheduling.  Speed batches of the thread-per-seed kernel with enough targets run as dynamic chains (one launch,
-  // restarts claimed on the device); everything else as static (target, chunk) jobs.
+  // ---- scheduling.  Speed batches of the thread-per-seed kernel with enough targets (a quarter of the resident lanes:
+  // below that the static schedule's private candidate records beat the shared-record protocol, measured 5 000-8 192
+  // Panda targets) run as dynamic chains (one launch, restarts claimed on the device); everything else as static
+  // (target, chunk) jobs.
   const bool dyn = tile == 1 && speed && !per_attempt_records && !(o && o->chunks) && !(o && (o->flags & OPTIK_BATCH_STATIC)) &&
-                   T * 8 >= (uint64_t)plan0.resident_tiles && T < 0xfffffffeull && R <= UNBOUNDED_RESTARTS;
+                   T * 4 >= (uint64_t)plan0.resident_tiles && T < 0xfffffffeull && R <= UNBOUNDED_RESTARTS;
   uint64_t C = o ? o->chunks : 0;
   if (per_attempt_records) C = R;
   if (dyn) C = 1;

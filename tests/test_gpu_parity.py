@@ -682,7 +682,7 @@ def test_cpp_consumer_end_to_end(name, tmp_path):
     assert dik == solved  # diff_ik always has a solution (alpha = 0 at worst)
 
 
-@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 6000, 24),
+@pytest.mark.parametrize("name,T,R", [("panda", 20000, 16), ("ur5", 150000, 32), ("ur3e", 12000, 8), ("panda", 10000, 24),
                                       ("panda", 70000, 32)])
 def test_dynamic_speed_batches_equal_static_schedule(name, T, R):
     """Speed batches run as dynamic chains (restarts claimed on the device, idle lanes help unsolved targets in
@@ -718,7 +718,7 @@ def test_dynamic_speed_batches_equal_static_schedule(name, T, R):
             assert int(e3["restart"][t]) == ref["restart"] and np.array_equal(q3[t], ref["q"])
 
 
-@pytest.mark.parametrize("name,T,R", [("panda", 12000, 6), ("panda", 38000, 32), ("ur3e", 9000, 64)])
+@pytest.mark.parametrize("name,T,R", [("panda", 12000, 6), ("panda", 38000, 32), ("ur3e", 10000, 64)])
 def test_dynamic_speed_batches_are_repeatable(name, T, R):
     """Shared targets (record word, restart counters, tickets, in-warp speculation) under repetition: the timing of
     helpers differs from launch to launch, the per-target answer must not -- 12 launches, both column layouts, each
@@ -980,10 +980,10 @@ def test_device_path_flags_clamped_seeds():
     import torch
     r, ch = robot_and_chain("panda")
     rng = np.random.default_rng(9)
-    T = 5000
+    T = 10000  # enough targets for the dynamic schedule
     tg = torch.from_numpy(targets_for(ch, rng, 64)).cuda().repeat(T // 64 + 1, 1)[:T].contiguous()
     x0 = torch.from_numpy(rng.uniform(ch.lb, ch.ub, size=(T, ch.n))).cuda()
-    bad = [3, 77, 4999]
+    bad = [3, 77, 9999]
     for t in bad:
         x0[t, t % ch.n] = ch.ub[t % ch.n] + 0.5
     cfg = ob.SolverConfig(max_time=0.0, max_restarts=16)
@@ -1004,7 +1004,7 @@ def test_device_path_flags_clamped_seeds():
         assert not np.any(sb.cpu().numpy() & ob.STATUS_FLAG_SEED_CLAMPED)
 
 
-@pytest.mark.parametrize("T", [600, 9000])
+@pytest.mark.parametrize("T", [600, 12000])
 def test_batch_default_budget_runs_until_max_time(T):
     """The reference's default budget -- no restart limit, max_time bounds the call (config.rs:52-65, lib.rs:260-277) --
     on the batched path: reachable targets are solved, unreachable ones keep drawing restarts until the deadline

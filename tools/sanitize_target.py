@@ -29,7 +29,7 @@ for name in ("panda", "ur5", "snake20"):
     r.select_records(rec)
     if n <= 8:
         # dynamic Speed chains (enough targets to take that path), both column layouts; device path with clamped seeds
-        T = 6000
+        T = 10000
         tgd = r.eval_batch(torch.from_numpy(rng.uniform(lb, ub, size=(T, n))).cuda(), want=("ee",))["ee"].contiguous()
         x0d = torch.from_numpy(rng.uniform(lb, ub, size=(T, n))).cuda()
         x0d[5, 0] = ub[0] + 1.0

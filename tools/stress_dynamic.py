@@ -6,8 +6,8 @@ sys.path.insert(0, ".")
 import optik_b200 as ob
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 bad = 0
-for name, T, R in (("panda", 5000, 32), ("panda", 12000, 6), ("panda", 37000, 32), ("panda", 38000, 32), ("panda", 90000, 16),
-                   ("ur5", 20000, 32), ("ur5", 300000, 32), ("ur3e", 9000, 64), ("ur3e", 60000, 100)):
+for name, T, R in (("panda", 9500, 32), ("panda", 12000, 6), ("panda", 37000, 32), ("panda", 38000, 32), ("panda", 90000, 16),
+                   ("ur5", 20000, 32), ("ur5", 300000, 32), ("ur3e", 10000, 64), ("ur3e", 60000, 100)):
     r = ob.Robot.named(name)
     n = r.num_positions()
     lb, ub = [torch.tensor(x, dtype=torch.float64, device="cuda") for x in r.joint_limits()]
