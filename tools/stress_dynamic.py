@@ -7,7 +7,10 @@ import optik_b200 as ob
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 bad = 0
 for name, T, R in (("panda", 9500, 32), ("panda", 12000, 6), ("panda", 37000, 32), ("panda", 38000, 32), ("panda", 90000, 16),
-                   ("ur5", 20000, 32), ("ur5", 300000, 32), ("ur3e", 10000, 64), ("ur3e", 60000, 100)):
+                   ("ur5", 20000, 32), ("ur5", 300000, 32), ("ur3e", 10000, 64), ("ur3e", 60000, 100),
+                   # edges of the schedule: the dynamic threshold, exactly the resident lanes, one and two restarts
+                   ("panda", 9472, 1), ("panda", 9473, 2), ("panda", 37887, 3), ("panda", 37888, 1), ("panda", 37889, 5),
+                   ("panda", 50000, 1), ("ur5", 12629, 2), ("ur5", 56832, 3)):
     r = ob.Robot.named(name)
     n = r.num_positions()
     lb, ub = [torch.tensor(x, dtype=torch.float64, device="cuda") for x in r.joint_limits()]
