@@ -564,8 +564,9 @@ T1_HOT_UNROLL
                 for (int j = 0; j < n; j++) P.cand_q[tgt_id * n + j] = qt_[j * T1_THREADS];
                 P.cand_f[tgt_id] = ft; P.cand_status[tgt_id] = status;
                 if (P.cand_restart) P.cand_restart[tgt_id] = r_idx;
-                __threadfence();
-                *((volatile unsigned long long*)(P.dyn_word + tgt_id)) = (unsigned long long)pub << 32;
+                // release store: the row is visible before the word says "free" (a release fence, not the sequentially
+                // consistent one of __threadfence())
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.dyn_word + tgt_id), "l"((unsigned long long)pub << 32) : "memory");
                 break;
               }
               w = old;
